@@ -46,6 +46,51 @@ int b200enc_linear(const void* x, long long x_batch_stride, int ldx, const void*
                    int ldr, void* out, long long out_batch_stride, int ldo, int batches, int M, int N, int K,
                    int flags, void* stream);
 
+/* flags for b200enc_attention */
+#define B200ENC_ATTN_P_SMEM 1 /* debug: stage softmax probabilities through shared memory instead of TMEM */
+
+/*
+ * out[b][i][64h + :] = softmax_j( q[b][i][64h + :] . k[b][j][64h + :] * scale ) v[b][j][64h + :]
+ *
+ * Replaces F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0, is_causal=False) at
+ * transformer.py:52 together with the head split/merge views at :47-49 and :53: q, k, v are column slices of the
+ * projection output (row strides ldq / ldkv, head h at columns [64h, 64h+64)), the result is head-interleaved
+ * [B, Lq, H*64] ready for out_proj. head_dim must be 64 (every BASELINE config). Lq != Lkv is allowed
+ * (the 1-query MAP pooling head, image/vit.py:41).
+ */
+int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                      long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
+                      int H, int Lq, int Lkv, int head_dim, float scale, int flags, void* stream);
+
+/*
+ * out[r][:] = (x[r][:] - mean_r) * rsqrt(var_r + eps) * gamma + beta, biased variance (nn.LayerNorm:
+ * transformer.py:87,93; vit.py:69,83; whisper.py:27,33; bert.py:31,37). Row r of x starts at x + r*ldx elements, so a
+ * strided view (e.g. only the class-token rows, vit.py:20-22) can be normalised without a gather.
+ * stats (optional) receives (mean, rstd) pairs.
+ */
+int b200enc_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int d,
+                      void* out, long long ldo, float* stats, void* stream);
+
+/* stats[r] = (mean_r, rsqrt(var_r + eps)) only: the per-row half of a LayerNorm folded into the next GEMM. */
+int b200enc_row_stats(const void* x, long long ldx, float eps, int rows, int d, float* stats, void* stream);
+
+/* out[b][:] = mean over the L token rows of x[b] (GlobalAveragePooling, image/vit.py:25-27). */
+int b200enc_mean_tokens(const void* x, long long batch_stride, long long ldx, int B, int L, int d, void* out,
+                        long long ldo, void* stream);
+
+#define B200ENC_DTYPE_BF16 0
+#define B200ENC_DTYPE_F32 1
+
+/*
+ * rows[b*P + ph*(W/p) + pw][c*p*p + i*p + j] = img[b][c][ph*p + i][pw*p + j]  (NCHW image, 3 channels), bf16, row
+ * stride Kpad with zero padding: the A operand that turns nn.Conv2d(3, d, p, p) (image/vit.py:64,78) into
+ * b200enc_linear with w = conv.weight.view(d, 3*p*p).
+ */
+int b200enc_patch_rows(const void* img, int img_dtype, int B, int H, int W, int p, int Kpad, void* rows, void* stream);
+
+/* tokens[b][0][:] = cls[:] for every image (torch.cat([cls_token, out], -2) at image/vit.py:80-81). */
+int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, long long batch_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

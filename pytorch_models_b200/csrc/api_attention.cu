@@ -1,0 +1,55 @@
+// C-ABI entry point for the attention core (see include/b200enc.h).
+#include "../../include/b200enc.h"
+#include "attention.cuh"
+#include "host_util.h"
+
+using namespace b200;
+
+namespace {
+template <bool kPTmem>
+int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                     cudaStream_t s) {
+  auto kern = attention_kernel<kPTmem>;
+  constexpr int smem = att_smem_bytes<kPTmem>();
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int max_ctas = 2 * sm_count();
+  const int grid = p.n_items < max_ctas ? p.n_items : max_ctas;
+  kern<<<grid, ATT_THREADS, smem, s>>>(tq, tk, tv, p);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                                 long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo,
+                                 int B, int H, int Lq, int Lkv, int head_dim, float scale, int flags, void* stream) {
+  B200_CHECK_ARG(q && k && v && out, "b200enc_attention: null tensor pointer");
+  B200_CHECK_ARG(head_dim == ATT_HD, "b200enc_attention: head_dim=%d is not supported (only 64)", head_dim);
+  B200_CHECK_ARG(B >= 1 && H >= 1 && Lq >= 1 && Lkv >= 1, "b200enc_attention: bad shape B=%d H=%d Lq=%d Lkv=%d", B, H,
+                 Lq, Lkv);
+  B200_CHECK_ARG(ldq >= H * ATT_HD && ldkv >= H * ATT_HD && ldo >= H * ATT_HD,
+                 "b200enc_attention: leading dimension smaller than H*64");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && ldo % 8 == 0 && out_batch_stride % 8 == 0,
+                 "b200enc_attention: output rows must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  const long long qbs = B > 1 ? q_batch_stride : (long long)Lq * ldq;
+  const long long kbs = B > 1 ? kv_batch_stride : (long long)Lkv * ldkv;
+  if ((rc = make_tmap_bf16(&tq, q, uint64_t(H) * ATT_HD, Lq, B, ldq, qbs, ATT_HD, ATT_BQ, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tk, k, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, ATT_BKV, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tv, v, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, ATT_BKV, 128))) return rc;
+  AttnParams p;
+  p.B = B;
+  p.H = H;
+  p.Lq = Lq;
+  p.Lkv = Lkv;
+  p.n_qt = (Lq + ATT_BQ - 1) / ATT_BQ;
+  p.n_items = B * H * p.n_qt;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out_batch_stride = out_batch_stride;
+  p.ldo = ldo;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (flags & B200ENC_ATTN_P_SMEM) return launch_attention<false>(tq, tk, tv, p, s);
+  return launch_attention<true>(tq, tk, tv, p, s);
+}

@@ -1,0 +1,60 @@
+// Patch rows for the patch-embedding GEMM (reference: nn.Conv2d(3, d, p, p) at image/vit.py:64,78, stride == kernel,
+// followed by flatten(-2).transpose(-1,-2)): rows[b*P + ph*Wp + pw][c*p*p + i*p + j] = img[b][c][ph*p+i][pw*p+j],
+// columns [3*p*p, Kpad) zero-filled so the row stride is a multiple of 16 bytes (p = 14: 588 -> 592).
+// Also writes the class-token row of the token matrix (vit.py:80-81) when asked to.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+template <typename TIn, int V>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const TIn* __restrict__ img, int B, int H, int W, int p, int Kpad, __nv_bfloat16* __restrict__ rows) {
+  const int Wp = W / p, Hp = H / p;
+  const int wv = W / V;  // vector chunks per image row
+  const long long total = (long long)B * 3 * H * wv;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) {
+    const int xv = int(t % wv);
+    long long r = t / wv;
+    const int y = int(r % H);
+    r /= H;
+    const int c = int(r % 3);
+    const int b = int(r / 3);
+    const int x = xv * V;
+    const int ph = y / p, i = y - ph * p, pw = x / p, j = x - pw * p;
+    const TIn* src = img + (((long long)b * 3 + c) * H + y) * W + x;
+    __nv_bfloat16* dst = rows + ((long long)b * Hp * Wp + (long long)ph * Wp + pw) * Kpad + (c * p + i) * p + j;
+    __nv_bfloat16 tmp[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) tmp[k] = __float2bfloat16_rn(float(src[k]));
+    if (V == 8) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(tmp);
+    } else if (V == 2) {
+      *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(tmp);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = tmp[k];
+    }
+  }
+  // zero the padding columns
+  const int K = 3 * p * p;
+  const int pad = Kpad - K;
+  if (pad > 0) {
+    const long long nrows = (long long)B * Hp * Wp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = t; q < nrows * pad; q += stride) rows[(q / pad) * Kpad + K + (q % pad)] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// tokens[b][0][:] = cls[:]  (class token gets no positional embedding: vit.py:79-81)
+__global__ void __launch_bounds__(256)
+cls_rows_kernel(const __nv_bfloat16* __restrict__ cls, int B, int d, __nv_bfloat16* __restrict__ tokens,
+                long long batch_stride) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * d) return;
+  const int b = int(t / d), c = int(t % d);
+  tokens[(long long)b * batch_stride + c] = cls[c];
+}
+
+}  // namespace b200

@@ -239,6 +239,243 @@ static const LinearCase kLinearCases[] = {
     {"perf_qkv_direct", 1, 25216, 2304, 768, true, false, false, false, true, false, 0, 16, 20},
 };
 
+
+// ------------------------------------------------------------------------------------------ attention
+struct AttnCase {
+  const char* name;
+  int B, H, Lq, Lkv;
+  bool self_qkv;  // q/k/v are slices of one fused [B, L, 3*H*64] buffer
+  bool p_smem;
+  float mag;
+  int check_bh;  // number of (b,h) pairs checked (0 = all)
+  int time_iters;
+};
+
+static bool run_attn(const AttnCase& c) {
+  printf("attention %s: B=%d H=%d Lq=%d Lkv=%d self=%d p_smem=%d\n", c.name, c.B, c.H, c.Lq, c.Lkv, c.self_qkv,
+         c.p_smem);
+  fflush(stdout);
+  const int B = c.B, H = c.H, Lq = c.Lq, Lkv = c.Lkv, D = H * 64;
+  std::vector<uint16_t> hq, hkv;
+  int ldq, ldkv;
+  size_t koff, voff;
+  if (c.self_qkv) {
+    hq = rand_bf16(size_t(B) * Lq * 3 * D, c.mag, false);
+    ldq = ldkv = 3 * D;
+    koff = D;
+    voff = 2 * D;
+  } else {
+    hq = rand_bf16(size_t(B) * Lq * D, c.mag, false);
+    hkv = rand_bf16(size_t(B) * Lkv * 2 * D, c.mag, false);
+    ldq = D;
+    ldkv = 2 * D;
+    koff = 0;
+    voff = D;
+  }
+  DevBuf dq(hq.size() * 2), dkv(hkv.size() * 2 + 16), dout(size_t(B) * Lq * D * 2);
+  CK(cudaMemcpy(dq.p, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice));
+  if (!c.self_qkv) CK(cudaMemcpy(dkv.p, hkv.data(), hkv.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout.p, 0x7f, dout.bytes));
+  const uint16_t* kvbase_h = c.self_qkv ? hq.data() : hkv.data();
+  uint16_t* kvbase_d = (uint16_t*)(c.self_qkv ? dq.p : dkv.p);
+  const float scale = 0.125f;
+  auto call = [&]() {
+    return b200enc_attention(dq.p, (long long)Lq * ldq, ldq, kvbase_d + koff, kvbase_d + voff, (long long)Lkv * ldkv,
+                             ldkv, dout.p, (long long)Lq * D, D, B, H, Lq, Lkv, 64, scale,
+                             c.p_smem ? B200ENC_ATTN_P_SMEM : 0, nullptr);
+  };
+  int rc = call();
+  if (rc) {
+    printf("  [FAIL] b200enc_attention rc=%d: %s\n", rc, b200enc_last_error());
+    return false;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("  [FAIL] kernel error: %s\n", cudaGetErrorString(e));
+    return false;
+  }
+  std::vector<uint16_t> ho(size_t(B) * Lq * D);
+  CK(cudaMemcpy(ho.data(), dout.p, ho.size() * 2, cudaMemcpyDeviceToHost));
+  CmpStat st;
+  const int nbh = B * H;
+  const int stepbh = (c.check_bh > 0 && c.check_bh < nbh) ? nbh / c.check_bh : 1;
+  std::vector<double> sc(Lkv);
+  for (int bh = 0; bh < nbh; bh += stepbh) {
+    const int b = bh / H, h = bh % H;
+    for (int i = 0; i < Lq; ++i) {
+      const uint16_t* qr = &hq[(size_t(b) * Lq + i) * ldq + h * 64];
+      double mx = -1e300;
+      for (int j = 0; j < Lkv; ++j) {
+        const uint16_t* kr = kvbase_h + (size_t(b) * Lkv + j) * ldkv + koff + h * 64;
+        double a = 0;
+        for (int t = 0; t < 64; ++t) a += double(bf2f(qr[t])) * double(bf2f(kr[t]));
+        sc[j] = a * scale;
+        mx = sc[j] > mx ? sc[j] : mx;
+      }
+      double den = 0;
+      for (int j = 0; j < Lkv; ++j) {
+        sc[j] = exp(sc[j] - mx);
+        den += sc[j];
+      }
+      for (int t = 0; t < 64; ++t) {
+        double o = 0;
+        for (int j = 0; j < Lkv; ++j)
+          o += sc[j] * double(bf2f(kvbase_h[(size_t(b) * Lkv + j) * ldkv + voff + h * 64 + t]));
+        o /= den;
+        cmp_one(st, o, bf2f(ho[(size_t(b) * Lq + i) * D + h * 64 + t]), 0.01 * c.mag, 0.02, i, h * 64 + t, c.name);
+      }
+    }
+  }
+  bool ok = report(c.name, st);
+  if (ok && c.time_iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) call();
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < c.time_iters; ++i) call();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= c.time_iters;
+    const double fl = 4.0 * B * H * double(Lq) * Lkv * 64;
+    const double bytes = 2.0 * B * D * (2.0 * Lq + 2.0 * Lkv);
+    printf("  time %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s (algorithmic)\n", c.name, ms, fl / ms * 1e-9,
+           bytes / ms * 1e-6);
+    fflush(stdout);
+  }
+  return ok;
+}
+
+static const AttnCase kAttnCases[] = {
+    // name        B   H   Lq    Lkv   self  psmem mag  bh iters
+    {"l64_smem", 1, 1, 64, 64, true, true, 1.0f, 0, 0},
+    {"l64_tmem", 1, 1, 64, 64, true, false, 1.0f, 0, 0},
+    {"l128_smem", 2, 2, 128, 128, true, true, 1.0f, 0, 0},
+    {"l128_tmem", 2, 2, 128, 128, true, false, 1.0f, 0, 0},
+    {"l197_smem", 2, 3, 197, 197, true, true, 2.0f, 0, 0},
+    {"l197_tmem", 2, 3, 197, 197, true, false, 2.0f, 0, 0},
+    {"l576_tmem", 1, 2, 576, 576, true, false, 2.0f, 0, 0},
+    {"l1370_tmem", 1, 2, 1370, 1370, true, false, 3.0f, 1, 0},
+    {"cross_q1", 3, 2, 1, 576, false, false, 2.0f, 0, 0},
+    {"many_items", 40, 12, 197, 197, true, false, 2.0f, 6, 0},
+    {"perf_vitb", 128, 12, 197, 197, true, false, 1.0f, 2, 20},
+    {"perf_vitb_smem", 128, 12, 197, 197, true, true, 1.0f, 2, 20},
+    {"perf_whisper", 8, 20, 1500, 1500, true, false, 1.0f, 1, 10},
+    {"perf_siglip", 32, 16, 576, 576, true, false, 1.0f, 1, 10},
+};
+
+// ------------------------------------------------------------------------------------------ layernorm / stats
+static bool run_layernorm(int rows, int d, float eps, int row_mult, int iters) {
+  printf("layernorm rows=%d d=%d eps=%g row_mult=%d\n", rows, d, eps, row_mult);
+  const long long ldx = (long long)d * row_mult;
+  auto hx = rand_bf16(size_t(rows) * ldx, 2.0f, false);
+  for (size_t i = 0; i < hx.size(); ++i) hx[i] = f2bf(bf2f(hx[i]) + 0.7f);  // non-zero mean
+  auto hg = rand_f32(d, 1.0f), hb = rand_f32(d, 0.5f);
+  DevBuf dx(hx.size() * 2), dg(d * 4), db(d * 4), dout(size_t(rows) * d * 2), dst(size_t(rows) * 8), dst2(size_t(rows) * 8);
+  CK(cudaMemcpy(dx.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dg.p, hg.data(), d * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db.p, hb.data(), d * 4, cudaMemcpyHostToDevice));
+  int rc = b200enc_layernorm(dx.p, ldx, (float*)dg.p, (float*)db.p, eps, rows, d, dout.p, d, (float*)dst.p, nullptr);
+  if (!rc) rc = b200enc_row_stats(dx.p, ldx, eps, rows, d, (float*)dst2.p, nullptr);
+  if (rc) {
+    printf("  [FAIL] rc=%d: %s\n", rc, b200enc_last_error());
+    return false;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("  [FAIL] kernel error: %s\n", cudaGetErrorString(e));
+    return false;
+  }
+  std::vector<uint16_t> ho(size_t(rows) * d);
+  std::vector<float> hs(size_t(rows) * 2), hs2(size_t(rows) * 2);
+  CK(cudaMemcpy(ho.data(), dout.p, ho.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hs.data(), dst.p, hs.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hs2.data(), dst2.p, hs2.size() * 4, cudaMemcpyDeviceToHost));
+  CmpStat st, ss;
+  const int step = rows > 512 ? rows / 512 : 1;
+  for (int r = 0; r < rows; r += step) {
+    const uint16_t* xr = &hx[size_t(r) * ldx];
+    double m = 0, v = 0;
+    for (int k = 0; k < d; ++k) m += bf2f(xr[k]);
+    m /= d;
+    for (int k = 0; k < d; ++k) v += (bf2f(xr[k]) - m) * (bf2f(xr[k]) - m);
+    v /= d;
+    const double rstd = 1.0 / sqrt(v + eps);
+    cmp_one(ss, m, hs[2 * r], 1e-5, 1e-5, r, 0, "mean");
+    cmp_one(ss, rstd, hs[2 * r + 1], 1e-5, 1e-4, r, 1, "rstd");
+    cmp_one(ss, m, hs2[2 * r], 1e-5, 1e-5, r, 2, "mean2");
+    cmp_one(ss, rstd, hs2[2 * r + 1], 1e-5, 1e-4, r, 3, "rstd2");
+    for (int k = 0; k < d; ++k)
+      cmp_one(st, (bf2f(xr[k]) - m) * rstd * hg[k] + hb[k], bf2f(ho[size_t(r) * d + k]), 0.01, 0.008, r, k, "ln");
+  }
+  bool ok = report("layernorm", st);
+  ok = report("row_stats", ss) && ok;
+  if (ok && iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i)
+      b200enc_layernorm(dx.p, ldx, (float*)dg.p, (float*)db.p, eps, rows, d, dout.p, d, nullptr, nullptr);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    printf("  time layernorm: %.3f ms  %.1f GB/s\n", ms, 4.0 * rows * d / ms * 1e-6);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) b200enc_row_stats(dx.p, ldx, eps, rows, d, (float*)dst2.p, nullptr);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    printf("  time row_stats: %.3f ms  %.1f GB/s\n", ms, 2.0 * rows * d / ms * 1e-6);
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------ patch rows
+static bool run_patch(int B, int HW, int p, bool f32) {
+  const int Kp = (3 * p * p + 7) / 8 * 8, P = (HW / p) * (HW / p);
+  printf("patch_rows B=%d HW=%d p=%d f32=%d Kpad=%d\n", B, HW, p, f32, Kp);
+  const size_t n = size_t(B) * 3 * HW * HW;
+  std::vector<float> hf(n);
+  std::vector<uint16_t> hb(n);
+  for (size_t i = 0; i < n; ++i) {
+    hf[i] = urand() * 2;
+    hb[i] = f2bf(hf[i]);
+  }
+  DevBuf dimg(n * 4), drows(size_t(B) * P * Kp * 2);
+  if (f32)
+    CK(cudaMemcpy(dimg.p, hf.data(), n * 4, cudaMemcpyHostToDevice));
+  else
+    CK(cudaMemcpy(dimg.p, hb.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(drows.p, 0x7f, drows.bytes));
+  int rc = b200enc_patch_rows(dimg.p, f32 ? B200ENC_DTYPE_F32 : B200ENC_DTYPE_BF16, B, HW, HW, p, Kp, drows.p, nullptr);
+  if (rc) {
+    printf("  [FAIL] rc=%d: %s\n", rc, b200enc_last_error());
+    return false;
+  }
+  CK(cudaDeviceSynchronize());
+  std::vector<uint16_t> hr(size_t(B) * P * Kp);
+  CK(cudaMemcpy(hr.data(), drows.p, hr.size() * 2, cudaMemcpyDeviceToHost));
+  CmpStat st;
+  const int Wp = HW / p;
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < P; ++t)
+      for (int k = 0; k < Kp; ++k) {
+        double want = 0;
+        if (k < 3 * p * p) {
+          const int c = k / (p * p), i = (k / p) % p, j = k % p, ph = t / Wp, pw = t % Wp;
+          want = bf2f(hb[((size_t(b) * 3 + c) * HW + ph * p + i) * HW + pw * p + j]);
+        }
+        cmp_one(st, want, bf2f(hr[(size_t(b) * P + t) * Kp + k]), 0, 0, b * P + t, k, "patch");
+      }
+  return report("patch_rows", st);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("usage: %s <case>|list\n", argv[0]);
@@ -247,6 +484,8 @@ int main(int argc, char** argv) {
   std::string which = argv[1];
   if (which == "list") {
     for (auto& c : kLinearCases) printf("linear:%s\n", c.name);
+    for (auto& c : kAttnCases) printf("attn:%s\n", c.name);
+    printf("rows:all\n");
     return 0;
   }
   cudaDeviceProp prop;
@@ -258,6 +497,25 @@ int main(int argc, char** argv) {
       found = true;
       ok = run_linear(c) && ok;
     }
+  }
+  for (auto& c : kAttnCases) {
+    if (which == std::string("attn:") + c.name || which == "attn:all") {
+      found = true;
+      ok = run_attn(c) && ok;
+    }
+  }
+  if (which == "rows:all") {
+    found = true;
+    ok = run_layernorm(1000, 768, 1e-6f, 1, 0) && ok;
+    ok = run_layernorm(333, 192, 1e-5f, 1, 0) && ok;
+    ok = run_layernorm(77, 1280, 1e-5f, 1, 0) && ok;
+    ok = run_layernorm(64, 1024, 1e-6f, 5, 0) && ok;  // strided rows (class-token gather)
+    ok = run_layernorm(201728, 768, 1e-6f, 1, 20) && ok;
+    ok = run_patch(2, 224, 16, false) && ok;
+    ok = run_patch(2, 224, 16, true) && ok;
+    ok = run_patch(1, 518, 14, false) && ok;
+    ok = run_patch(1, 518, 14, true) && ok;
+    ok = run_patch(2, 64, 8, false) && ok;
   }
   if (!found) {
     printf("unknown case %s\n", which.c_str());
