@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: ViT-B/16 @ 224 bf16 forward throughput (images/s) of the B200-native encoder path.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU forward (oracle port) on host cores
+
+A step = one forward of the model over one batch of synthetic images (BASELINE.json configs[1]: ViT-B/16 augreg 224,
+197 tokens, 1024 images per GPU, random-init weights). Prints ONE JSON line (rank 0). See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (constructor, per-GPU batch, input shape, kind, n_heads for the oracle, pool, tokens per sample)
+    "c2": dict(desc="ViT-B/16 augreg 224px (197 tokens), bf16", batch=1024, shape=(3, 224, 224), kind="vit",
+               make=lambda pm: pm.ViT.from_google("B/16"), heads=12, pool="cls_token", L=197, layers=12, d=768, P=196, p=16),
+    "c3": dict(desc="ViT-L/16 SigLIP 384px (576 tokens), bf16", batch=256, shape=(3, 384, 384), kind="vit",
+               make=lambda pm: pm.ViT.from_google("L/16_siglip", img_size=384), heads=16, pool="mha", L=576, layers=24,
+               d=1024, P=576, p=16),
+    "c4": dict(desc="DINOv2 L/14 518px (1370 tokens), bf16", batch=128, shape=(3, 518, 518), kind="vit",
+               make=lambda pm: pm.ViT.from_facebook("L/14_dinov2"), heads=16, pool="cls_token", L=1370, layers=24,
+               d=1024, P=1369, p=14),
+    "c5": dict(desc="Whisper large-v3 encoder (3000 mel frames -> 1500 tokens), bf16", batch=64, shape=(128, 3000),
+               kind="whisper", make=lambda pm: pm.WhisperEncoder(32, 1280, 128), heads=20, pool=None, L=1500, layers=32,
+               d=1280, P=0, p=0),
+}
+
+
+def flops_per_sample(c: dict) -> float:
+    """Algorithmic FLOPs: F_embed + layers * (24 L d^2 + 4 L^2 d); biases/LN/GELU/softmax excluded."""
+    L, d = c["L"], c["d"]
+    if c["kind"] == "vit":
+        embed = 2.0 * c["P"] * (3 * c["p"] ** 2) * d
+    else:
+        embed = 2.0 * 3000 * 128 * 3 * d + 2.0 * 1500 * d * 3 * d
+    return embed + c["layers"] * (24.0 * L * d * d + 4.0 * L * L * d)
+
+
+def synthetic_weights_(model: torch.nn.Module, seed: int) -> None:
+    """Random-init weights of the named architecture (no checkpoints offline): default nn init under manual_seed(0)
+    plus seeded noise in the tensors the architecture zero/one-initialises (cls_token, pe, pos_embs, LayerNorm)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            parts = k.split(".")
+            is_norm = len(parts) >= 2 and "norm" in parts[-2]
+            if k in ("cls_token", "pe", "pos_embs", "pooler.probe"):
+                v.copy_(0.02 * torch.randn(v.shape, generator=g))
+            elif is_norm and parts[-1] == "weight":
+                v.copy_(1.0 + 0.1 * torch.randn(v.shape, generator=g))
+            elif is_norm and parts[-1] == "bias":
+                v.copy_(0.1 * torch.randn(v.shape, generator=g))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.lines: list[str] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), smax.append(float(f[1])), power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(source="measured", burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"])
+    return dict(source="fallback", burst=1590.0, sustained=1400.0, hbm=6650.0)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_forward_fn(cfg: dict, n_samples: int):
+    """The reference's CPU path (fp32, all host threads) as restated by oracle/oracle_torch.py on the same config."""
+    import pytorch_models_b200 as pm
+    from oracle import oracle_torch  # the CPU arm is the one place bench.py may execute the oracle
+
+    torch.manual_seed(0)
+    model = cfg["make"](pm).eval()
+    synthetic_weights_(model, 100)
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    torch.manual_seed(1)
+    x = torch.randn(n_samples, *cfg["shape"])
+
+    @torch.no_grad()
+    def run():
+        if cfg["kind"] == "vit":
+            return oracle_torch.vit_forward(sd, x, cfg["heads"], cfg["pool"])
+        return oracle_torch.whisper_encoder_forward(sd, x)
+
+    return run
+
+
+def cpu_sample_size(name: str) -> int:
+    return {"c2": 32, "c3": 4, "c4": 2, "c5": 1}[name]
+
+
+def time_cpu(cfg: dict, name: str, steps: int, warmup: int) -> tuple[float, int, int]:
+    n = cpu_sample_size(name)
+    run = cpu_forward_fn(cfg, n)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return dt, n, torch.get_num_threads()
+
+
+def run_reference_arm(args, cfg: dict) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    dt, n, threads = time_cpu(cfg, args.config, args.steps, args.warmup)
+    value = n / dt
+    line = {
+        "impl": "reference", "metric": "ViT-B/16 img/s bf16" if args.config == "c2" else f"{args.config} samples/s bf16",
+        "value": value, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": cfg["desc"], "arm": "reference CPU forward, fp32", "sample_images_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} images per step, fp32, torch CPU ops ({threads} threads), oracle/oracle_torch.py"},
+        "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--chunk", type=int, default=256, help="images per H2D/compute pipeline chunk in the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    import torch.distributed as dist
+
+    import pytorch_models_b200 as pm
+    from pytorch_models_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    B = args.batch or cfg["batch"]
+
+    torch.manual_seed(0)
+    model = cfg["make"](pm).eval()
+    synthetic_weights_(model, 100)
+    model = model.to(dev).bfloat16()
+    torch.manual_seed(1 + rank)
+    x_host = torch.randn(B, *cfg["shape"]).bfloat16().pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value")
+    with torch.no_grad():
+        for _ in range(warmup):
+            y = model(x_dev)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        launches0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            y = model(x_dev)
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = ops.LAUNCHES - launches0
+        clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host images -> H2D -> forward -> D2H embeddings, chunks pipelined over two streams
+    e2e = None
+    if not args.no_e2e:
+        chunk = min(args.chunk, B)
+        n_chunks = (B + chunk - 1) // chunk
+        copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        out_dim = y.shape[1:]
+        out_host = torch.empty(B, *out_dim, dtype=torch.bfloat16).pin_memory()
+        stage = [torch.empty(chunk, *cfg["shape"], device=dev, dtype=torch.bfloat16) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_step():
+            for ci in range(n_chunks):
+                lo, hi = ci * chunk, min(B, (ci + 1) * chunk)
+                s = ci % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[s])
+                    stage[s][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                    ready[s].record(copy_stream)
+                with torch.cuda.stream(comp_stream):
+                    comp_stream.wait_event(ready[s])
+                    out = model(stage[s][: hi - lo])
+                    freed[s].record(comp_stream)
+                    out_host[lo:hi].copy_(out, non_blocking=True)
+
+        with torch.no_grad():
+            for s in range(2):
+                freed[s].record(comp_stream)
+            for _ in range(warmup):
+                e2e_step()
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t0.record(copy_stream)
+            comp_stream.wait_event(t0)
+            for _ in range(steps):
+                e2e_step()
+            copy_stream.wait_stream(comp_stream)
+            t1.record(copy_stream)
+            barrier()
+            e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / steps
+        e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "img/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+               "d2h_bytes_per_step": out_host.numel() * out_host.element_size(),
+               "pipeline": f"{n_chunks} chunks of {chunk} images, copy/compute on two streams"}
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), per-launch CUDA events on the launching stream
+    roofline = None
+    if rank == 0:
+        with torch.no_grad():
+            rec = ops.profile(True)
+            model(x_dev)
+            torch.cuda.synchronize()
+            ops.profile(False)
+        by_kernel: dict[str, list[float]] = {}
+        gemm_ms = gemm_flops = 0.0
+        for name, meta, a, b in rec:
+            ms = a.elapsed_time(b)
+            by_kernel.setdefault(name, [0.0, 0])
+            by_kernel[name][0] += ms
+            by_kernel[name][1] += 1
+            if name == "b200enc_linear":
+                gemm_ms += ms
+                gemm_flops += 2.0 * meta["batches"] * meta["M"] * meta["N"] * meta["K"]
+        peaks = measured_peaks()
+        total_ms = sum(v[0] for v in by_kernel.values())
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "gemm_bf16_kernel (b200enc_linear: QKV / out_proj / FC1 / FC2 / patch embed)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["sustained"], "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['burst']})",
+            "frac_of_burst": achieved / peaks["burst"], "traffic": None,
+            "launches_per_step": by_kernel["b200enc_linear"][1], "avg_launch_ms": gemm_ms / by_kernel["b200enc_linear"][1],
+            "share_of_step": gemm_ms / total_ms,
+            "step_breakdown_ms": {k: round(v[0], 3) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
+        }
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port of the reference's CPU forward on a bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        dt, n, threads = time_cpu(cfg, args.config, steps=2, warmup=1)
+        cpu_baseline = {"value": n / dt, "unit": "img/s", "cores": threads, "kind": "port",
+                        "sample": f"{n} images x 2 timed passes, fp32, torch CPU ops, oracle/oracle_torch.py"}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        fl = flops_per_sample(cfg)
+        line = {
+            "metric": "ViT-B/16 img/s bf16" if args.config == "c2" else f"{args.config} samples/s bf16",
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "per_gpu_batch": B, "global_batch": B * world,
+                       "parallelism": f"dp{world} (batch-sharded, no collective)", "weights": "random-init, seed 0",
+                       "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"},
+            "tokens_per_s": value * cfg["L"],
+            "model_tflops": value * fl / 1e12, "model_frac_of_burst_peak": value * fl / 1e12 / world / peaks["burst"],
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

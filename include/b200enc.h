@@ -91,6 +91,14 @@ int b200enc_patch_rows(const void* img, int img_dtype, int B, int H, int W, int 
 /* tokens[b][0][:] = cls[:] for every image (torch.cat([cls_token, out], -2) at image/vit.py:80-81). */
 int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, long long batch_stride, void* stream);
 
+/*
+ * rows[n][t + 1][c] = x[n][c][t], rows[n][0] = rows[n][T + 1] = 0   (x: (N, C, T) fp32/bf16 -> (N, T+2, C) bf16).
+ * Time-major, zero-padded input of the Whisper conv stem (nn.Conv1d(k=3, pad=1) at audio2text/whisper.py:16-21): output
+ * step t of a stride-s convolution reads the 3*C contiguous values starting at row s*t, so each convolution is a
+ * b200enc_linear call over an overlapping strided view with w[n][k*C + c] = conv.weight[n][c][k].
+ */
+int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, void* rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

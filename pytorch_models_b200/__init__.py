@@ -1,0 +1,10 @@
+"""pytorch_models_b200: B200-native (sm_100a) implementation of the encoder-block hot path of
+gau-nernst/pytorch-models — ``transformer.py`` (LayerNorm, MHA, MLP) plus the ViT patch embedding — behind the
+reference's module API. Kernels live in ``csrc/`` and are reached through the C-ABI in ``include/b200enc.h``."""
+from . import _lib, ops
+from .audio2text import WhisperEncoder
+from .image import ViT
+from .text import BERT
+from .transformer import MHA, MLP, Encoder, EncoderLayer
+
+__all__ = ["MHA", "MLP", "Encoder", "EncoderLayer", "ViT", "WhisperEncoder", "BERT", "ops", "_lib"]

@@ -1,0 +1,80 @@
+"""ctypes binding of libb200enc.so (the C-ABI declared in include/b200enc.h).
+
+There is no fallback: if the shared library has not been built (``python -c 'import __graft_entry__ as g; g.build()'``
+or ``make -C pytorch_models_b200/csrc``) every kernel call raises. PyTorch only owns the buffers and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200enc.so")
+
+LINEAR_GELU = 1
+LINEAR_DIRECT_STORE = 256
+ATTN_P_SMEM = 1
+DTYPE_BF16 = 0
+DTYPE_F32 = 1
+
+_lib = None
+
+_SIGNATURES = {
+    "b200enc_version": (c_int, []),
+    "b200enc_last_error": (ctypes.c_char_p, []),
+    "b200enc_linear": (
+        c_int,
+        [c_void_p, c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+         c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    ),
+    "b200enc_attention": (
+        c_int,
+        [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int,
+         c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    ),
+    "b200enc_layernorm": (
+        c_int,
+        [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p],
+    ),
+    "b200enc_row_stats": (c_int, [c_void_p, c_longlong, c_float, c_int, c_int, c_void_p, c_void_p]),
+    "b200enc_mean_tokens": (
+        c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p]),
+    "b200enc_patch_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200enc_cls_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p]),
+    "b200enc_time_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class B200EncError(RuntimeError):
+    """A non-zero return from libb200enc (argument errors map to ValueError in `check`)."""
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raise if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200EncError(
+            f"{LIB_PATH} not found: the sm_100a extension is not built and there is no CPU/PyTorch fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` from the repository root."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = load().b200enc_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise ValueError(f"{what}: {msg}")
+    raise B200EncError(f"{what}: CUDA error {rc}: {msg}")

@@ -34,7 +34,8 @@ extern "C" int b200enc_linear(const void* x, long long x_batch_stride, int ldx, 
   B200_CHECK_ARG(batches >= 1 && M >= 1 && N >= 1 && K >= 1, "b200enc_linear: bad shape batches=%d M=%d N=%d K=%d",
                  batches, M, N, K);
   B200_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "b200enc_linear: K=%d and N=%d must be multiples of 8", K, N);
-  B200_CHECK_ARG(ldx >= K && ldw >= K && ldo >= N, "b200enc_linear: leading dimension smaller than the row length");
+  // ldx < K is allowed on purpose: overlapping rows express a strided 1-D convolution as a GEMM (whisper stem).
+  B200_CHECK_ARG(ldx >= 8 && ldw >= K && ldo >= N, "b200enc_linear: leading dimension smaller than the row length");
   B200_CHECK_ARG((colsum == nullptr) == (rowstats == nullptr),
                  "b200enc_linear: colsum and rowstats must be given together (LayerNorm fold)");
   if (residual) {

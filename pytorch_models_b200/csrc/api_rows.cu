@@ -95,3 +95,18 @@ extern "C" int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, lon
   B200_CUDA(cudaGetLastError());
   return 0;
 }
+
+extern "C" int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, void* rows, void* stream) {
+  B200_CHECK_ARG(x && rows && N >= 1 && C >= 1 && T >= 1, "b200enc_time_rows: bad arguments");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, N);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(rows);
+  if (dtype == B200ENC_DTYPE_BF16)
+    time_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, T, dst);
+  else if (dtype == B200ENC_DTYPE_F32)
+    time_rows_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), C, T, dst);
+  else
+    return set_error(-1, "b200enc_time_rows: unsupported dtype %d", dtype);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -57,4 +57,34 @@ cls_rows_kernel(const __nv_bfloat16* __restrict__ cls, int B, int d, __nv_bfloat
   tokens[(long long)b * batch_stride + c] = cls[c];
 }
 
+// Whisper stem input (audio2text/whisper.py:16-21,30): x (N, C, T) channel-major -> rows (N, T+2, C) time-major bf16,
+// rows 0 and T+1 zero. A k=3, pad=1 Conv1d over time then reads, for output step t, the 3*C contiguous values that
+// start at row t (stride 1) or 2t (stride 2): the convolution becomes a plain GEMM over an overlapping strided view.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+time_rows_kernel(const TIn* __restrict__ x, int C, int T, __nv_bfloat16* __restrict__ rows) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const TIn* xn = x + (long long)n * C * T;
+  __nv_bfloat16* rn = rows + (long long)n * (T + 2) * C;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? float(xn[(long long)c * T + t]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < C) rn[(long long)(t + 1) * C + c] = __float2bfloat16_rn(tile[tx][i]);
+  }
+  if (blockIdx.x == 0 && ty == 0) {
+    const int c = c0 + tx;
+    if (c < C) {
+      rn[c] = __float2bfloat16_rn(0.f);
+      rn[(long long)(T + 1) * C + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
 }  // namespace b200

@@ -1,0 +1,223 @@
+"""Thin Python wrappers over the C-ABI: one function per libb200enc entry point.
+
+All tensors must be CUDA bf16 (fp32 for vectors / statistics); the wrappers only validate, fetch raw pointers and the
+current stream, and call into the library. No arithmetic happens in PyTorch here.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+LAUNCHES = 0  # kernels launched through the C-ABI by this process (every entry point launches exactly one)
+_PROFILE: list | None = None  # when a list: (entry point, meta, start event, end event) per launch
+
+
+def profile(enable: bool) -> list | None:
+    """Start (returns the record list) or stop per-launch CUDA-event timing on the launching stream."""
+    global _PROFILE
+    _PROFILE = [] if enable else None
+    return _PROFILE
+
+
+def _call(name: str, meta: dict | None, *args) -> None:
+    global LAUNCHES
+    fn = getattr(_lib.load(), name)
+    rec = _PROFILE
+    if rec is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        rec.append((name, meta, e0, e1))
+    LAUNCHES += 1
+    _lib.check(rc, name)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Tensor | None) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback "
+                f"(got a {t.device} tensor)"
+            )
+
+
+def _need(t: Tensor | None, dtype: torch.dtype, name: str) -> None:
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def linear(
+    x: Tensor,
+    w: Tensor,
+    bias: Tensor | None,
+    out: Tensor,
+    *,
+    colsum: Tensor | None = None,
+    rowstats: Tensor | None = None,
+    residual: Tensor | None = None,
+    gelu: bool = False,
+    direct_store: bool = False,
+) -> Tensor:
+    """out[b, m, :] = epilogue(x[b, m, :] @ w.T); x, out, residual are (batches, M, *) views with unit inner stride.
+
+    A residual with a leading dimension of 1 is broadcast over the batch (positional embedding).
+    """
+    _need_cuda(x, w, bias, out, colsum, rowstats, residual)
+    _need(x, torch.bfloat16, "x"), _need(w, torch.bfloat16, "w"), _need(out, torch.bfloat16, "out")
+    _need(bias, torch.float32, "bias"), _need(colsum, torch.float32, "colsum"), _need(rowstats, torch.float32, "rowstats")
+    _need(residual, torch.bfloat16, "residual")
+    if x.dim() == 2:
+        x, out = x.unsqueeze(0), out.unsqueeze(0)
+        residual = None if residual is None else residual.unsqueeze(0)
+    batches, M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or out.shape != (batches, M, N):
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)}, w {tuple(w.shape)}, out {tuple(out.shape)}")
+    if x.stride(2) != 1 or w.stride(1) != 1 or out.stride(2) != 1:
+        raise ValueError("inner strides must be 1")
+    res_bs, ldr = 0, 0
+    if residual is not None:
+        if residual.shape[-2:] != (M, N) or residual.stride(2) != 1:
+            raise ValueError(f"residual shape {tuple(residual.shape)} does not match ({M}, {N})")
+        res_bs = 0 if residual.shape[0] == 1 else residual.stride(0)
+        ldr = residual.stride(1)
+    if rowstats is not None and (not rowstats.is_contiguous() or rowstats.numel() != 2 * batches * M):
+        raise ValueError("rowstats must be a contiguous (batches*M, 2) tensor")
+    flags = (_lib.LINEAR_GELU if gelu else 0) | (_lib.LINEAR_DIRECT_STORE if direct_store else 0)
+    _call(
+        "b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=colsum is not None, gelu=gelu, res=residual is not None),
+        x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum), _ptr(rowstats),
+        _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1), batches, M, N, K, flags, _stream(),
+    )
+    return out
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, *, p_smem: bool = False) -> Tensor:
+    """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64)."""
+    _need_cuda(q, k, v, out)
+    for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _need(t, torch.bfloat16, name)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise ValueError(f"{name} must be a (B, L, H*head_dim) view with unit inner stride")
+    B, Lq, D = q.shape
+    Lkv = k.shape[1]
+    if D % n_heads != 0:
+        raise ValueError("width not divisible by n_heads")
+    if k.shape != v.shape or k.stride() != v.stride() or k.shape[0] != B or k.shape[2] != D or out.shape != q.shape:
+        raise ValueError("q/k/v/out shapes or strides are inconsistent")
+    _call(
+        "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv),
+        q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),
+        out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
+        _lib.ATTN_P_SMEM if p_smem else 0, _stream(),
+    )
+    return out
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, out: Tensor, stats: Tensor | None = None) -> Tensor:
+    """x: (rows, d) view (any row stride), out: (rows, d)."""
+    _need_cuda(x, gamma, beta, out, stats)
+    _need(x, torch.bfloat16, "x"), _need(out, torch.bfloat16, "out")
+    _need(gamma, torch.float32, "gamma"), _need(beta, torch.float32, "beta"), _need(stats, torch.float32, "stats")
+    rows, d = x.shape
+    if x.stride(1) != 1 or out.stride(1) != 1 or out.shape != x.shape:
+        raise ValueError("layernorm expects (rows, d) views with unit inner stride")
+    _call(
+        "b200enc_layernorm", dict(rows=rows, d=d),
+        x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps), rows, d, out.data_ptr(),
+        out.stride(0), _ptr(stats), _stream(),
+    )
+    return out
+
+
+def row_stats(x: Tensor, eps: float, stats: Tensor) -> Tensor:
+    _need_cuda(x, stats)
+    _need(x, torch.bfloat16, "x"), _need(stats, torch.float32, "stats")
+    rows, d = x.shape
+    if x.stride(1) != 1 or stats.numel() != 2 * rows or not stats.is_contiguous():
+        raise ValueError("row_stats expects a (rows, d) view and a contiguous (rows, 2) stats tensor")
+    _call(
+        "b200enc_row_stats", dict(rows=rows, d=d),
+        x.data_ptr(), x.stride(0), float(eps), rows, d, stats.data_ptr(), _stream()
+    )
+    return stats
+
+
+def mean_tokens(x: Tensor, out: Tensor) -> Tensor:
+    _need_cuda(x, out)
+    _need(x, torch.bfloat16, "x"), _need(out, torch.bfloat16, "out")
+    B, L, d = x.shape
+    if x.stride(2) != 1 or out.shape != (B, d) or out.stride(1) != 1:
+        raise ValueError("mean_tokens expects x (B, L, d) and out (B, d)")
+    _call(
+        "b200enc_mean_tokens", None,
+        x.data_ptr(), x.stride(0), x.stride(1), B, L, d, out.data_ptr(), out.stride(0),
+                                         _stream()
+    )
+    return out
+
+
+def patch_rows(imgs: Tensor, patch: int, kpad: int, rows: Tensor) -> Tensor:
+    _need_cuda(imgs, rows)
+    if imgs.dtype == torch.bfloat16:
+        dt = _lib.DTYPE_BF16
+    elif imgs.dtype == torch.float32:
+        dt = _lib.DTYPE_F32
+    else:
+        raise TypeError(f"images must be bfloat16 or float32, got {imgs.dtype}")
+    if imgs.dim() != 4 or imgs.shape[1] != 3 or not imgs.is_contiguous():
+        raise ValueError("images must be a contiguous (N, 3, H, W) tensor")
+    _need(rows, torch.bfloat16, "rows")
+    B, _, H, W = imgs.shape
+    _call(
+        "b200enc_patch_rows", None,
+        imgs.data_ptr(), dt, B, H, W, patch, kpad, rows.data_ptr(), _stream()
+    )
+    return rows
+
+
+def cls_rows(cls: Tensor, tokens: Tensor) -> Tensor:
+    _need_cuda(cls, tokens)
+    _need(cls, torch.bfloat16, "cls"), _need(tokens, torch.bfloat16, "tokens")
+    B, _, d = tokens.shape
+    _call(
+        "b200enc_cls_rows", None,
+        cls.data_ptr(), B, d, tokens.data_ptr(), tokens.stride(0), _stream()
+    )
+    return tokens
+
+
+def time_rows(x: Tensor, rows: Tensor) -> Tensor:
+    """x: (N, C, T) fp32/bf16 -> rows (N, T + 2, C) bf16 with zero first/last rows (conv padding)."""
+    _need_cuda(x, rows)
+    if x.dtype == torch.bfloat16:
+        dt = _lib.DTYPE_BF16
+    elif x.dtype == torch.float32:
+        dt = _lib.DTYPE_F32
+    else:
+        raise TypeError(f"input must be bfloat16 or float32, got {x.dtype}")
+    if x.dim() != 3 or not x.is_contiguous() or not rows.is_contiguous():
+        raise ValueError("time_rows expects contiguous (N, C, T) input and (N, T+2, C) output")
+    N, C, T = x.shape
+    if rows.shape != (N, T + 2, C):
+        raise ValueError(f"rows must have shape {(N, T + 2, C)}")
+    _need(rows, torch.bfloat16, "rows")
+    _call(
+        "b200enc_time_rows", None,
+        x.data_ptr(), dt, N, C, T, rows.data_ptr(), _stream()
+    )
+    return rows

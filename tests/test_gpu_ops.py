@@ -1,0 +1,124 @@
+"""Per-kernel GPU tests through the C-ABI (ctypes): each op against the same op in fp32 PyTorch on the same bf16-rounded
+inputs. Tolerances are bf16 output rounding (2^-9 relative) plus accumulation-order noise."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _close(got, want, atol, rtol):
+    err = (got.float() - want.float()).abs()
+    bound = atol + rtol * want.float().abs()
+    assert bool((err <= bound).all()), f"max err {err.max().item():.4g}, worst excess {(err - bound).max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (130, 576, 192), (257, 768, 3072), (1000, 2304, 768), (77, 1280, 5120)])
+@pytest.mark.parametrize("mode", ["bias", "gelu", "residual", "fold", "fold_gelu"])
+def test_linear(M, N, K, mode):
+    from pytorch_models_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ref = x.float() @ w.float().T
+    if mode.startswith("fold"):
+        stats = torch.stack([torch.randn(M, device="cuda", generator=g) * 0.3,
+                             torch.rand(M, device="cuda", generator=g) + 0.5], dim=1).contiguous()
+        s = w.float().sum(1)
+        ops.linear(x, w, b, out, colsum=s, rowstats=stats, gelu=mode.endswith("gelu"))
+        ref = stats[:, 1:2] * (ref - stats[:, 0:1] * s[None]) + b
+        if mode.endswith("gelu"):
+            ref = F.gelu(ref)
+    elif mode == "residual":
+        r = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+        ops.linear(x, w, b, out, residual=r)
+        ref = ref + b + r.float()
+    else:
+        ops.linear(x, w, b, out, gelu=mode == "gelu")
+        ref = ref + b
+        if mode == "gelu":
+            ref = F.gelu(ref)
+    _close(out, ref, 0.02, 0.01)
+
+
+@pytest.mark.parametrize("L", [1, 5, 64, 128, 129, 197, 257, 576, 1370, 1500])
+def test_attention_matches_sdpa(L):
+    from pytorch_models_b200 import ops
+
+    B, H = 2, 3
+    g = torch.Generator(device="cuda").manual_seed(L)
+    qkv = (torch.randn(B, L, 3 * H * 64, device="cuda", generator=g) * 1.5).bfloat16()
+    out = torch.empty(B, L, H * 64, device="cuda", dtype=torch.bfloat16)
+    q, k, v = qkv[:, :, : H * 64], qkv[:, :, H * 64: 2 * H * 64], qkv[:, :, 2 * H * 64:]
+    ops.attention(q, k, v, out, H, 0.125)
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(k), heads(v)).transpose(1, 2).flatten(-2)
+    _close(out, want, 0.02, 0.02)
+
+
+def test_cross_attention_one_query():
+    """The MAP-pooling shape (vit.py:41): 1 query row against L keys."""
+    from pytorch_models_b200 import ops
+
+    B, H, L = 3, 2, 576
+    q = torch.randn(B, 1, H * 64, device="cuda").bfloat16()
+    kv = torch.randn(B, L, 2 * H * 64, device="cuda").bfloat16()
+    out = torch.empty(B, 1, H * 64, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, kv[:, :, : H * 64], kv[:, :, H * 64:], out, H, 0.125)
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(kv[:, :, : H * 64]), heads(kv[:, :, H * 64:]))
+    _close(out, want.transpose(1, 2).flatten(-2), 0.02, 0.02)
+
+
+@pytest.mark.parametrize("rows,d,eps", [(1, 64, 1e-5), (333, 192, 1e-6), (1000, 768, 1e-6), (77, 1280, 1e-5), (50, 768, 1e-12)])
+def test_layernorm_and_row_stats(rows, d, eps):
+    from pytorch_models_b200 import ops
+
+    x = (torch.randn(rows, d, device="cuda") * 2 + 0.7).bfloat16()
+    gmm, bta = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    out = torch.empty_like(x)
+    stats = torch.empty(rows, 2, device="cuda")
+    ops.layernorm(x, gmm, bta, eps, out, stats)
+    want = F.layer_norm(x.float(), (d,), gmm, bta, eps)
+    _close(out, want, 0.02, 0.01)
+    stats2 = torch.empty(rows, 2, device="cuda")
+    ops.row_stats(x, eps, stats2)
+    mean = x.float().mean(1)
+    rstd = (x.float().var(1, unbiased=False) + eps).rsqrt()
+    for s in (stats, stats2):
+        torch.testing.assert_close(s[:, 0], mean, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(s[:, 1], rstd, atol=1e-5, rtol=1e-4)
+
+
+def test_bad_arguments_raise():
+    from pytorch_models_b200 import ops
+
+    x = torch.randn(4, 60, device="cuda").bfloat16()  # K not a multiple of 8
+    w = torch.randn(8, 60, device="cuda").bfloat16()
+    with pytest.raises(ValueError):
+        ops.linear(x, w, None, torch.empty(4, 8, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        ops.linear(x.cpu(), w, None, torch.empty(4, 8, device="cuda", dtype=torch.bfloat16))
+    q = torch.randn(1, 4, 96, device="cuda").bfloat16()
+    with pytest.raises(ValueError):  # head_dim 32
+        ops.attention(q, q, q, torch.empty_like(q), 3, 1.0)
+
+
+@pytest.mark.parametrize("case", ["linear:tails_tma", "linear:embed_like", "linear:fold_gelu", "attn:l197_tmem",
+                                  "attn:cross_q1", "rows:all"])
+def test_native_selftest(case):
+    """The stand-alone C++ harness (fp64 CPU check inside the binary) on its edge-case shapes."""
+    exe = os.path.join(ROOT, "pytorch_models_b200", "b200enc_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("self-test binary not built")
+    r = subprocess.run([exe, case], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
