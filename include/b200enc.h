@@ -35,16 +35,43 @@ const char* b200enc_last_error(void);
  *
  *   epi(acc) = acc + bias[n]                                        (colsum == NULL)
  *            = rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]           (LayerNorm folded into the GEMM: w must be
- *              gamma-scaled, colsum[n] = sum_k w[n][k], bias[n] = W.beta + b; rowstats = (mean, rstd) pairs)
+ *              gamma-scaled, colsum[n] = sum_k w[n][k], bias[n] = W.beta + b)
  *   then GELU if flags & B200ENC_LINEAR_GELU, then + residual[b][m][n] if residual != NULL
  *   (res_batch_stride == 0 broadcasts one [M, N] table over the batch: the positional embedding).
  *
- * Strides are in elements. K and N must be multiples of 8; rows 16-byte aligned.
+ * Row statistics of the folded LayerNorm come in one of two forms:
+ *   rowstats_parts == 0 : rowstats[b*M + m] = (mean, rstd)                  (written by b200enc_row_stats)
+ *   rowstats_parts  > 0 : rowstats[(b*M + m)*parts + t] = (mean_t, M2_t) of columns [128t, 128t+128) of row m of x,
+ *                         as written through `stats_out` by the b200enc_linear call that produced x; they are
+ *                         combined in a fixed order (Chan's parallel variance) with ln_eps. parts = ceil(K/128) <= 12.
+ * stats_out (optional, needs a residual epilogue): per-128-column (mean, M2) of the bf16-rounded OUTPUT rows, laid
+ * out [(b*M + m)][ceil(N/128)] — the fused replacement of the row pass of the next LayerNorm.
+ *
+ * Strides are in elements. K and N must be multiples of 8; rows 16-byte aligned. x rows may overlap (ldx < K).
  */
-int b200enc_linear(const void* x, long long x_batch_stride, int ldx, const void* w, int ldw, const float* bias,
-                   const float* colsum, const float* rowstats, const void* residual, long long res_batch_stride,
-                   int ldr, void* out, long long out_batch_stride, int ldo, int batches, int M, int N, int K,
-                   int flags, void* stream);
+typedef struct b200enc_linear_args {
+  const void* x;               /* bf16 [batches][M][K], row stride ldx, batch stride x_batch_stride */
+  long long x_batch_stride;
+  int ldx;
+  const void* w;               /* bf16 [N][K], row stride ldw */
+  int ldw;
+  const float* bias;           /* fp32 [N] or NULL */
+  const float* colsum;         /* fp32 [N] or NULL (LayerNorm fold) */
+  const float* rowstats;       /* fp32 pairs, see above; required iff colsum != NULL */
+  int rowstats_parts;
+  float ln_eps;
+  const void* residual;        /* bf16 [batches or 1][M][N] or NULL */
+  long long res_batch_stride;
+  int ldr;
+  void* out;                   /* bf16 [batches][M][N] */
+  long long out_batch_stride;
+  int ldo;
+  float* stats_out;            /* fp32 pairs [(batches*M)][ceil(N/128)] or NULL */
+  int batches, M, N, K;
+  int flags;
+} b200enc_linear_args;
+
+int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
 /* flags for b200enc_attention */
 #define B200ENC_ATTN_P_SMEM 1 /* debug: stage softmax probabilities through shared memory instead of TMEM */

@@ -20,14 +20,27 @@ DTYPE_F32 = 1
 
 _lib = None
 
+
+class LinearArgs(ctypes.Structure):
+    """Mirror of ``b200enc_linear_args`` in include/b200enc.h."""
+
+    _fields_ = [
+        ("x", c_void_p), ("x_batch_stride", c_longlong), ("ldx", c_int),
+        ("w", c_void_p), ("ldw", c_int),
+        ("bias", c_void_p), ("colsum", c_void_p),
+        ("rowstats", c_void_p), ("rowstats_parts", c_int), ("ln_eps", c_float),
+        ("residual", c_void_p), ("res_batch_stride", c_longlong), ("ldr", c_int),
+        ("out", c_void_p), ("out_batch_stride", c_longlong), ("ldo", c_int),
+        ("stats_out", c_void_p),
+        ("batches", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+        ("flags", c_int),
+    ]
+
+
 _SIGNATURES = {
     "b200enc_version": (c_int, []),
     "b200enc_last_error": (ctypes.c_char_p, []),
-    "b200enc_linear": (
-        c_int,
-        [c_void_p, c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
-         c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
-    ),
+    "b200enc_linear": (c_int, [ctypes.POINTER(LinearArgs), c_void_p]),
     "b200enc_attention": (
         c_int,
         [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int,

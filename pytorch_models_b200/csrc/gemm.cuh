@@ -2,9 +2,10 @@
 //
 //   warp 0      : TMA producer (A/W tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
-//   warps 2..5  : epilogue (tcgen05.ld -> registers -> bias / LayerNorm-fold / erf-GELU / residual -> bf16 ->
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> bias / LayerNorm-fold / erf-GELU / residual -> bf16 ->
 //                 swizzled smem -> TMA store), overlapped with the next tile's main loop through two
-//                 256-column TMEM accumulators.
+//                 256-column TMEM accumulators. Two warps per TMEM lane quarter, each owning 128 of the 256
+//                 columns, so every SM sub-partition has two epilogue warps to hide latencies with.
 //
 // This one kernel serves every linear on the encoder path (reference call sites: transformer.py:47-49 fused QKV,
 // transformer.py:53 out_proj, transformer.py:59-67 MLP, vit.py:78 patch embedding as a GEMM over patch rows).
@@ -17,13 +18,15 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_STAT_SLICE = 128;  // columns per partial LayerNorm statistic
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 32 * 128;  // one staging buffer: 32 rows x 64 bf16
 constexpr int GEMM_SMEM_RING = GEMM_STAGES * GEMM_STAGE_BYTES;
-constexpr int GEMM_SMEM_STG = 4 * 2 * GEMM_STG_BYTES;     // 4 epilogue warps x 2 buffers
+constexpr int GEMM_SMEM_STG = GEMM_EPI_WARPS * GEMM_STG_BYTES;  // one staging buffer per epilogue warp
 constexpr int GEMM_SMEM_COLVEC = 2 * GEMM_BN * 4;         // bias|c and colsum for one tile
 constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_RING + GEMM_SMEM_STG + GEMM_SMEM_COLVEC + 256;
 
@@ -36,7 +39,11 @@ struct GemmParams {
   int tiles_n;
   const float* bias;         // [N]  bias, or the folded constant vector c when ln_fold
   const float* colsum;       // [N]  s_n = sum_k W'[n][k] (ln_fold only)
-  const float2* rowstats;    // [batches*M] (mean, rstd) (ln_fold only)
+  const float2* rowstats;    // ln_fold only: [batches*M] (mean, rstd) when stat_parts == 0, else
+                             // [batches*M][stat_parts] partial (mean_t, M2_t) over 128-column slices of the row
+  int stat_parts;
+  float ln_eps;
+  float2* stats_out;         // kStats: [batches*M][ceil(N/128)] partial (mean_t, M2_t) of the OUTPUT rows
   const __nv_bfloat16* res;  // residual / positional table, nullptr if unused
   long long res_batch_stride;  // elements; 0 => same table for every batch (positional embedding)
   int ldr;                     // residual row stride (elements)
@@ -59,7 +66,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-fabsf(x), fast_exp2(q), fmaxf(x, 0.0f));
 }
 
-template <bool kFold, bool kGelu, bool kRes, bool kTmaStore>
+template <bool kFold, bool kGelu, bool kRes, bool kTmaStore, bool kStats>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -91,7 +98,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -166,92 +173,144 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int e = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
-    const uint32_t stg = stg_base + (warp - 2) * (2 * GEMM_STG_BYTES);
-    uint8_t* stg_ptr = smem + GEMM_SMEM_RING + (warp - 2) * (2 * GEMM_STG_BYTES);
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;        // which 128-column half of the tile this warp owns
+    const int e = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
+    const uint32_t stg = stg_base + (warp - 2) * GEMM_STG_BYTES;
+    uint8_t* stg_ptr = smem + GEMM_SMEM_RING + (warp - 2) * GEMM_STG_BYTES;
     float* cv_b = colvec;
     float* cv_s = colvec + GEMM_BN;
+    const int n_slices = (p.N + GEMM_STAT_SLICE - 1) / GEMM_STAT_SLICE;
     uint32_t acc = 0, acc_phase = 0;
-    uint32_t buf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       const int m0 = (r / p.tiles_n) * GEMM_BM;
       const int n0 = (r % p.tiles_n) * GEMM_BN;
-
-      named_bar_sync(1, 128);  // everyone finished reading the previous tile's column vectors
-      for (int i = e; i < GEMM_BN; i += 128) {
-        const int n = n0 + i;
-        cv_b[i] = (n < p.N && p.bias != nullptr) ? __ldg(p.bias + n) : 0.0f;
-        if (kFold) cv_s[i] = (n < p.N) ? __ldg(p.colsum + n) : 0.0f;
-      }
-      named_bar_sync(1, 128);
-
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      float rstd = 1.0f, nmr = 0.0f;  // nmr = -mean * rstd
-      if (kFold && row_ok) {
-        const float2 st = __ldg(p.rowstats + (long long)b * p.M + row);
-        rstd = st.y;
-        nmr = -st.x * st.y;
+      const int nh = n0 + hf * 128;  // first column owned by this warp
+
+      // ---- issue every global load of this tile up front: they complete while the tile's main loop still runs
+      float my_b = 0.0f, my_s = 0.0f;
+      if (n0 + e < p.N) {
+        if (p.bias != nullptr) my_b = __ldg(p.bias + n0 + e);
+        if (kFold) my_s = __ldg(p.colsum + n0 + e);
       }
-      const __nv_bfloat16* res_row = nullptr;
-      if (kRes) res_row = p.res + (long long)b * p.res_batch_stride + (long long)row * p.ldr + n0;
+      float2 st_full = make_float2(0.0f, 1.0f);
+      constexpr int kMaxParts = 12;
+      float2 st_part[kMaxParts];
+      if (kFold && row_ok) {
+        const long long grow = (long long)b * p.M + row;
+        if (p.stat_parts == 0) {
+          st_full = __ldg(p.rowstats + grow);
+        } else {
+#pragma unroll
+          for (int t = 0; t < kMaxParts; ++t)
+            if (t < p.stat_parts) st_part[t] = __ldg(p.rowstats + grow * p.stat_parts + t);
+        }
+      }
+      uint4 rres[2][8];
+      if (kRes) {
+        const __nv_bfloat16* res_row = p.res + (long long)b * p.res_batch_stride + (long long)row * p.ldr + nh;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            rres[cc][j] = make_uint4(0, 0, 0, 0);
+            if (row_ok && nh + cc * 64 + j * 8 < p.N)
+              rres[cc][j] = __ldg(reinterpret_cast<const uint4*>(res_row + cc * 64) + j);
+          }
+      }
+
+      named_bar_sync(1, 32 * GEMM_EPI_WARPS);  // everyone finished reading the previous tile's column vectors
+      cv_b[e] = my_b;
+      if (kFold) cv_s[e] = my_s;
+      named_bar_sync(1, 32 * GEMM_EPI_WARPS);
+
+      float rstd = 1.0f, nmr = 0.0f;  // nmr = -mean * rstd
+      if (kFold) {
+        if (p.stat_parts == 0) {
+          rstd = st_full.y;
+          nmr = -st_full.x * st_full.y;
+        } else if (row_ok) {
+          // combine the per-slice (mean, M2) written by the producing GEMM's epilogue (Chan et al.), fixed order
+          float mean = 0.0f;
+#pragma unroll
+          for (int t = 0; t < kMaxParts; ++t)
+            if (t < p.stat_parts) mean += float(min(GEMM_STAT_SLICE, p.K - t * GEMM_STAT_SLICE)) * st_part[t].x;
+          mean /= float(p.K);
+          float m2 = 0.0f;
+#pragma unroll
+          for (int t = 0; t < kMaxParts; ++t)
+            if (t < p.stat_parts) {
+              const float dm = st_part[t].x - mean;
+              m2 += st_part[t].y + float(min(GEMM_STAT_SLICE, p.K - t * GEMM_STAT_SLICE)) * dm * dm;
+            }
+          rstd = rsqrtf(m2 / float(p.K) + p.ln_eps);
+          nmr = -mean * rstd;
+        }
+      }
+      float st_shift = 0.0f, st_s1 = 0.0f, st_s2 = 0.0f;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * GEMM_BN + (uint32_t(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * GEMM_BN + hf * 128 + (uint32_t(q * 32) << 16);
 
-#pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 64; ++c) {
-        const int nc = n0 + c * 64;
-        if (nc >= p.N) break;
-        uint4 rres[8];
-        if (kRes) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            rres[j] = make_uint4(0, 0, 0, 0);
-            if (row_ok && nc + j * 8 < p.N) rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64) + j);
-          }
-        }
+      for (int cc = 0; cc < 2; ++cc) {
+        const int nc = nh + cc * 64;
+        if (nc >= p.N) break;
         uint32_t v0[32], v1[32];
-        tmem_ld32(taddr + c * 64, v0);
-        tmem_ld32(taddr + c * 64 + 32, v1);
+        tmem_ld32(taddr + cc * 64, v0);
+        tmem_ld32(taddr + cc * 64 + 32, v1);
         tmem_wait_ld();
 
         uint32_t packed[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x0, x1;
-          {
-            const int col = c * 64 + 2 * j;
-            const float a0 = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
-            const float a1 = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j + 1 - 32]);
-            if (kFold) {
-              x0 = fmaf(rstd, a0, fmaf(nmr, cv_s[col], cv_b[col]));
-              x1 = fmaf(rstd, a1, fmaf(nmr, cv_s[col + 1], cv_b[col + 1]));
-            } else {
-              x0 = a0 + cv_b[col];
-              x1 = a1 + cv_b[col + 1];
-            }
-          }
-          if (kGelu) {
-            x0 = gelu_erf_fast(x0);
-            x1 = gelu_erf_fast(x1);
+        for (int j4 = 0; j4 < 16; ++j4) {
+          // 4 columns per step: column vectors come from smem as one broadcast 16-byte load each
+          const float4 cb = *reinterpret_cast<const float4*>(cv_b + hf * 128 + cc * 64 + 4 * j4);
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kFold) cs = *reinterpret_cast<const float4*>(cv_s + hf * 128 + cc * 64 + 4 * j4);
+          float x[4];
+          const float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
+          const float csv[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = 4 * j4 + u;
+            const float a = __uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]);
+            x[u] = kFold ? fmaf(rstd, a, fmaf(nmr, csv[u], cbv[u])) : a + cbv[u];
+            if (kGelu) x[u] = gelu_erf_fast(x[u]);
           }
           if (kRes) {
-            const uint32_t rr = reinterpret_cast<const uint32_t*>(rres)[j];
-            x0 += bf16_lo(rr);
-            x1 += bf16_hi(rr);
+            const uint32_t r0 = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4];
+            const uint32_t r1 = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + 1];
+            x[0] += bf16_lo(r0);
+            x[1] += bf16_hi(r0);
+            x[2] += bf16_lo(r1);
+            x[3] += bf16_hi(r1);
           }
-          packed[j] = pack_bf16x2(x0, x1);
+          packed[2 * j4] = pack_bf16x2(x[0], x[1]);
+          packed[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
+          if (kStats) {
+            // statistics of the values as stored (bf16-rounded), shifted by the row's first value in this slice
+            const float y[4] = {bf16_lo(packed[2 * j4]), bf16_hi(packed[2 * j4]), bf16_lo(packed[2 * j4 + 1]),
+                                bf16_hi(packed[2 * j4 + 1])};
+            if (cc == 0 && j4 == 0) st_shift = y[0];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float dlt = (nc + 4 * j4 + u < p.N) ? y[u] - st_shift : 0.0f;
+              st_s1 += dlt;
+              st_s2 = fmaf(dlt, dlt, st_s2);
+            }
+          }
         }
 
         if (kTmaStore) {
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store out of this buffer has drained
           __syncwarp();
-          uint8_t* dst = stg_ptr + buf * GEMM_STG_BYTES + lane * 128;
+          uint8_t* dst = stg_ptr + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) =
@@ -260,10 +319,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmC, stg + buf * GEMM_STG_BYTES, nc, m0 + q * 32, b);
+            tma_store_3d(&tmC, stg, nc, m0 + q * 32, b);
             tma_store_commit();
           }
-          buf ^= 1u;
         } else {
           if (row_ok) {
             __nv_bfloat16* orow = p.out + (long long)b * p.out_batch_stride + (long long)row * p.ldo + nc;
@@ -275,6 +333,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+      }
+      if (kStats && row_ok && nh < p.N) {
+        const float nt = float(min(GEMM_STAT_SLICE, p.N - nh));
+        const float mean_t = st_shift + st_s1 / nt;
+        const float m2_t = fmaxf(st_s2 - st_s1 * st_s1 / nt, 0.0f);
+        p.stats_out[((long long)b * p.M + row) * n_slices + nh / GEMM_STAT_SLICE] = make_float2(mean_t, m2_t);
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       tc_fence_before();

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -145,12 +146,23 @@ static bool run_linear(const LinearCase& c) {
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));  // sentinel 0x7f7f = 3.39e38 in bf16
 
   const int flags = (c.gelu ? B200ENC_LINEAR_GELU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0);
+  const int n_slices = (N + 127) / 128;
+  const bool want_stats = c.res && !c.fold && !c.direct;
+  DevBuf dso(size_t(B) * M * n_slices * 8);
   auto call = [&]() {
-    return b200enc_linear(dx.p, (long long)M * K, K, dw.p, K, (const float*)db.p, c.fold ? (const float*)ds.p : nullptr,
-                          c.fold ? (const float*)dst.p : nullptr, c.res ? dr.p : nullptr,
-                          c.res_bcast ? 0 : (long long)M * N, N,
-                          (uint16_t*)dout.p + size_t(c.out_row_off) * N, (long long)Mo * N, N, B, M, N, K, flags,
-                          nullptr);
+    b200enc_linear_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = dx.p; a.x_batch_stride = (long long)M * K; a.ldx = K;
+    a.w = dw.p; a.ldw = K;
+    a.bias = (const float*)db.p;
+    a.colsum = c.fold ? (const float*)ds.p : nullptr;
+    a.rowstats = c.fold ? (const float*)dst.p : nullptr;
+    a.rowstats_parts = 0; a.ln_eps = 0.f;
+    a.residual = c.res ? dr.p : nullptr; a.res_batch_stride = c.res_bcast ? 0 : (long long)M * N; a.ldr = N;
+    a.out = (uint16_t*)dout.p + size_t(c.out_row_off) * N; a.out_batch_stride = (long long)Mo * N; a.ldo = N;
+    a.stats_out = want_stats ? (float*)dso.p : nullptr;
+    a.batches = B; a.M = M; a.N = N; a.K = K; a.flags = flags;
+    return b200enc_linear(&a, nullptr);
   };
   int rc = call();
   if (rc) {
@@ -198,6 +210,28 @@ static bool run_linear(const LinearCase& c) {
         }
   }
   bool ok = report(c.name, st);
+  if (want_stats) {
+    // fused partial LayerNorm statistics: (mean, M2) of every 128-column slice of the stored (bf16) output rows
+    std::vector<float> hso(size_t(B) * M * n_slices * 2);
+    CK(cudaMemcpy(hso.data(), dso.p, hso.size() * 4, cudaMemcpyDeviceToHost));
+    CmpStat ss;
+    for (int b = 0; b < B; ++b)
+      for (int m = 0; m < M; m += (M > 400 ? 7 : 1))
+        for (int t = 0; t < n_slices; ++t) {
+          const int w = std::min(128, N - t * 128);
+          double mu = 0, m2 = 0;
+          for (int k = 0; k < w; ++k) mu += bf2f(ho[(size_t(b) * Mo + c.out_row_off + m) * N + t * 128 + k]);
+          mu /= w;
+          for (int k = 0; k < w; ++k) {
+            const double dlt = bf2f(ho[(size_t(b) * Mo + c.out_row_off + m) * N + t * 128 + k]) - mu;
+            m2 += dlt * dlt;
+          }
+          const float* g = &hso[((size_t(b) * M + m) * n_slices + t) * 2];
+          cmp_one(ss, mu, g[0], 1e-4, 1e-4, b * M + m, t, "slice_mean");
+          cmp_one(ss, m2, g[1], 1e-2, 1e-3, b * M + m, t, "slice_m2");
+        }
+    ok = report("fused_stats", ss) && ok;
+  }
 
   if (ok && c.time_iters > 0) {
     cudaEvent_t e0, e1;

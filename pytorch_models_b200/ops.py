@@ -5,6 +5,8 @@ current stream, and call into the library. No arithmetic happens in PyTorch here
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 from torch import Tensor
 
@@ -71,15 +73,21 @@ def linear(
     residual: Tensor | None = None,
     gelu: bool = False,
     direct_store: bool = False,
+    ln_eps: float = 0.0,
+    stats_out: Tensor | None = None,
 ) -> Tensor:
     """out[b, m, :] = epilogue(x[b, m, :] @ w.T); x, out, residual are (batches, M, *) views with unit inner stride.
 
     A residual with a leading dimension of 1 is broadcast over the batch (positional embedding).
+    ``rowstats`` is either (batches*M, 2) = (mean, rstd) from `row_stats`, or (batches*M, parts, 2) partial
+    (mean, M2) per 128 input columns as written through ``stats_out`` by the linear that produced ``x``
+    (then ``ln_eps`` is required). ``stats_out``: (batches*M, ceil(N/128), 2) fp32, needs a residual epilogue.
     """
     _need_cuda(x, w, bias, out, colsum, rowstats, residual)
     _need(x, torch.bfloat16, "x"), _need(w, torch.bfloat16, "w"), _need(out, torch.bfloat16, "out")
     _need(bias, torch.float32, "bias"), _need(colsum, torch.float32, "colsum"), _need(rowstats, torch.float32, "rowstats")
-    _need(residual, torch.bfloat16, "residual")
+    _need(residual, torch.bfloat16, "residual"), _need(stats_out, torch.float32, "stats_out")
+    _need_cuda(stats_out)
     if x.dim() == 2:
         x, out = x.unsqueeze(0), out.unsqueeze(0)
         residual = None if residual is None else residual.unsqueeze(0)
@@ -95,13 +103,22 @@ def linear(
             raise ValueError(f"residual shape {tuple(residual.shape)} does not match ({M}, {N})")
         res_bs = 0 if residual.shape[0] == 1 else residual.stride(0)
         ldr = residual.stride(1)
-    if rowstats is not None and (not rowstats.is_contiguous() or rowstats.numel() != 2 * batches * M):
-        raise ValueError("rowstats must be a contiguous (batches*M, 2) tensor")
+    parts = 0
+    if rowstats is not None:
+        if not rowstats.is_contiguous() or rowstats.numel() % (2 * batches * M) != 0:
+            raise ValueError("rowstats must be a contiguous (batches*M, 2) or (batches*M, parts, 2) tensor")
+        parts = 0 if rowstats.dim() == 2 else rowstats.shape[1]
+    if stats_out is not None and (not stats_out.is_contiguous() or stats_out.numel() != 2 * batches * M * ((N + 127) // 128)):
+        raise ValueError("stats_out must be a contiguous (batches*M, ceil(N/128), 2) tensor")
     flags = (_lib.LINEAR_GELU if gelu else 0) | (_lib.LINEAR_DIRECT_STORE if direct_store else 0)
+    args = _lib.LinearArgs(
+        x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum),
+        _ptr(rowstats), parts, float(ln_eps), _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1),
+        _ptr(stats_out), batches, M, N, K, flags,
+    )
     _call(
         "b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=colsum is not None, gelu=gelu, res=residual is not None),
-        x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum), _ptr(rowstats),
-        _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1), batches, M, N, K, flags, _stream(),
+        ctypes.byref(args), _stream(),
     )
     return out
 

@@ -5,14 +5,16 @@ Same class names, constructor signatures, attribute names and ``state_dict`` key
 into ``layer.sa.q_proj.weight`` etc.) keep working. The arithmetic does not run in PyTorch: ``forward`` sequences
 hand-written sm_100a kernels from ``libb200enc.so``:
 
-    pre-norm layer (transformer.py:125-126), 7 launches
-        row_stats(x)                          -> (mean, rstd) of sa_norm      (transformer.py:87)
-        linear [3·inner, d], LayerNorm folded -> fused q|k|v                  (transformer.py:47-49)
+    pre-norm layer (transformer.py:125-126), 5 launches (+1 row_stats for the first layer of a stack)
+        linear [3·inner, d], LayerNorm folded -> fused q|k|v                  (transformer.py:87,47-49)
         attention                             -> softmax(q kᵀ/√64) v          (transformer.py:52)
-        linear out_proj + bias + residual     -> x1                           (transformer.py:53,125)
-        row_stats(x1)                                                         (transformer.py:93)
-        linear1, LayerNorm folded, erf-GELU   -> hidden                       (transformer.py:59-61)
-        linear2 + bias + residual             -> x2                           (transformer.py:66,126)
+        linear out_proj + bias + residual     -> x1 (+ partial LN statistics) (transformer.py:53,125)
+        linear1, LayerNorm folded, erf-GELU   -> hidden                       (transformer.py:93,59-61)
+        linear2 + bias + residual             -> x2 (+ partial LN statistics) (transformer.py:66,126)
+
+    The row statistics (mean, rstd) a folded LayerNorm needs are produced by the epilogue of the GEMM that wrote
+    its input (per-128-column (mean, M2) partials, combined in a fixed order by the consumer), so no separate pass
+    over the residual stream is needed after the first layer.
 
 Only what the kernels implement is accepted (self/cross attention without mask, head_dim 64, exact GELU, eval mode);
 anything else raises ``NotImplementedError`` — there is no PyTorch fallback.
@@ -28,6 +30,7 @@ from torch import Tensor, nn
 from . import ops
 
 _SUPPORTED_HEAD_DIM = 64
+_MAX_STAT_PARTS = 12  # libb200enc combines at most 12 partial statistics per row (d <= 1536)
 
 
 # ----------------------------------------------------------------------------------------------- weight packing
@@ -293,13 +296,21 @@ class EncoderLayer(nn.Module):
         inner = self.sa.n_heads * self.sa.head_dim
         M = B * L
         e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        parts = (d + 127) // 128
+        fused = self.pre_norm and parts <= _MAX_STAT_PARTS
         return SimpleNamespace(
             qkv=e(B, L, 3 * inner), att=e(B, L, inner), hidden=e(M, self.mlp.linear1.out_features), mid=e(M, d),
             tmp=None if self.pre_norm else e(M, d), stats=e(M, 2, dt=torch.float32),
+            parts_mid=e(M, parts, 2, dt=torch.float32) if fused else None,
+            parts_out=e(M, parts, 2, dt=torch.float32) if fused else None,
         )
 
-    def run(self, x3: Tensor, out3: Tensor, ws: SimpleNamespace) -> Tensor:
-        """x3 (B, L, d) bf16 contiguous -> out3 (same shape, must not alias x3)."""
+    def run(self, x3: Tensor, out3: Tensor, ws: SimpleNamespace, stats_in: Tensor | None = None,
+            want_stats: bool = False) -> Tensor | None:
+        """x3 (B, L, d) bf16 contiguous -> out3 (same shape, must not alias x3).
+
+        ``stats_in``: partial LayerNorm statistics of x3 written by the producing GEMM (else a row_stats pass runs).
+        Returns the partial statistics of out3 when ``want_stats`` (for the next layer's sa_norm), else None."""
         sa, mlp = self.sa, self.mlp
         sa.check_supported()
         mlp.check_supported()
@@ -314,13 +325,19 @@ class EncoderLayer(nn.Module):
         qkv2 = ws.qkv.view(M, 3 * inner)
         q, k, v = ws.qkv[:, :, :inner], ws.qkv[:, :, inner:2 * inner], ws.qkv[:, :, 2 * inner:]
         if self.pre_norm:
-            ops.row_stats(x2, self.sa_norm.eps, ws.stats)
-            ops.linear(x2, pq.w, pq.bias, qkv2, colsum=pq.colsum, rowstats=ws.stats)
+            if stats_in is None:
+                stats_in = ops.row_stats(x2, self.sa_norm.eps, ws.stats)
+            ops.linear(x2, pq.w, pq.bias, qkv2, colsum=pq.colsum, rowstats=stats_in, ln_eps=self.sa_norm.eps)
             ops.attention(q, k, v, ws.att, sa.n_heads, sa.scale)
-            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.mid, residual=x2)
-            ops.row_stats(ws.mid, self.mlp_norm.eps, ws.stats)
-            ops.linear(ws.mid, p1.w, p1.bias, ws.hidden, colsum=p1.colsum, rowstats=ws.stats, gelu=True)
-            ops.linear(ws.hidden, p2.w, p2.bias, out2, residual=ws.mid)
+            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.mid, residual=x2, stats_out=ws.parts_mid)
+            mid_stats = ws.parts_mid
+            if mid_stats is None:
+                mid_stats = ops.row_stats(ws.mid, self.mlp_norm.eps, ws.stats)
+            ops.linear(ws.mid, p1.w, p1.bias, ws.hidden, colsum=p1.colsum, rowstats=mid_stats,
+                       ln_eps=self.mlp_norm.eps, gelu=True)
+            out_stats = ws.parts_out if want_stats else None
+            ops.linear(ws.hidden, p2.w, p2.bias, out2, residual=ws.mid, stats_out=out_stats)
+            return out_stats
         else:  # post-norm (BERT): transformer.py:128-129
             g1, b1 = norm_vectors(self.sa_norm)
             g2, b2 = norm_vectors(self.mlp_norm)
@@ -331,7 +348,7 @@ class EncoderLayer(nn.Module):
             ops.linear(ws.mid, p1.w, p1.bias, ws.hidden, gelu=True)
             ops.linear(ws.hidden, p2.w, p2.bias, ws.tmp, residual=ws.mid)
             ops.layernorm(ws.tmp, g2, b2, self.mlp_norm.eps, out2)
-        return out3
+        return None
 
     def forward(self, x: Tensor) -> Tensor:
         d = self.sa_norm.normalized_shape[0]
@@ -382,9 +399,10 @@ class Encoder(nn.Sequential):
         B, L, _ = x3.shape
         ws = layers[0].workspace(B, L, x3.device)
         bufs = [torch.empty_like(x3), torch.empty_like(x3) if len(layers) > 1 else None]
-        cur = x3
+        cur, stats = x3, None
         for i, layer in enumerate(layers):
-            cur = layer.run(cur, bufs[i % 2], ws)
+            stats = layer.run(cur, bufs[i % 2], ws, stats_in=stats, want_stats=i + 1 < len(layers))
+            cur = bufs[i % 2]
         return cur
 
     def forward(self, x: Tensor) -> Tensor:

@@ -122,3 +122,37 @@ def test_native_selftest(case):
         pytest.skip("self-test binary not built")
     r = subprocess.run([exe, case], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("M,d,N", [(300, 768, 2304), (130, 192, 576), (64, 1280, 1280), (257, 1024, 4096)])
+def test_fused_layernorm_statistics_chain(M, d, N):
+    """Producer GEMM (+residual) emits per-128-column (mean, M2); the next GEMM folds LayerNorm from those partials.
+    Must agree with LayerNorm -> Linear computed in fp32 on the producer's (bf16) output."""
+    from pytorch_models_b200 import ops
+    from pytorch_models_b200.transformer import pack_folded
+
+    g = torch.Generator(device="cuda").manual_seed(d + M)
+    a = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    w0 = (torch.randn(d, d, device="cuda", generator=g) * d ** -0.5).bfloat16()
+    b0 = torch.randn(d, device="cuda", generator=g)
+    res = (torch.randn(M, d, device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    x = torch.empty(M, d, device="cuda", dtype=torch.bfloat16)
+    parts = torch.empty(M, (d + 127) // 128, 2, device="cuda")
+    ops.linear(a, w0, b0, x, residual=res, stats_out=parts)
+
+    lin = torch.nn.Linear(d, N).cuda()
+    norm = torch.nn.LayerNorm(d, 1e-6).cuda()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.1, generator=g)
+        norm.bias.normal_(0.0, 0.1, generator=g)
+        pk = pack_folded([lin], norm)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.linear(x, pk.w, pk.bias, out, colsum=pk.colsum, rowstats=parts, ln_eps=1e-6)
+        want = lin(norm(x.float()))
+        # the standalone statistics kernel must give the same result up to rounding
+        stats = torch.empty(M, 2, device="cuda")
+        ops.row_stats(x, 1e-6, stats)
+        out2 = torch.empty_like(out)
+        ops.linear(x, pk.w, pk.bias, out2, colsum=pk.colsum, rowstats=stats)
+    _close(out, want, 0.03, 0.02)
+    _close(out, out2, 0.01, 0.01)
