@@ -24,7 +24,8 @@ const char* b200enc_last_error(void);
 
 /* flags for b200enc_linear */
 #define B200ENC_LINEAR_GELU 1          /* exact (erf) GELU after bias: nn.GELU(), transformer.py:61 */
-#define B200ENC_LINEAR_DIRECT_STORE 256 /* debug: st.global epilogue instead of the TMA-store epilogue */
+#define B200ENC_LINEAR_DIRECT_STORE 256 /* debug: per-thread st.global epilogue without the smem transpose */
+#define B200ENC_LINEAR_ONE_CTA 512      /* debug: 128-row tiles on single CTAs instead of 256-row tiles on CTA pairs */
 
 /*
  * out[b][m][n] = epi( sum_k x[b][m][k] * w[n][k] )   for b < batches, m < M, n < N      (tcgen05 GEMM)
@@ -73,9 +74,6 @@ typedef struct b200enc_linear_args {
 
 int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
-/* flags for b200enc_attention */
-#define B200ENC_ATTN_P_SMEM 1 /* debug: stage softmax probabilities through shared memory instead of TMEM */
-
 /*
  * out[b][i][64h + :] = softmax_j( q[b][i][64h + :] . k[b][j][64h + :] * scale ) v[b][j][64h + :]
  *
@@ -83,7 +81,7 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
  * transformer.py:52 together with the head split/merge views at :47-49 and :53: q, k, v are column slices of the
  * projection output (row strides ldq / ldkv, head h at columns [64h, 64h+64)), the result is head-interleaved
  * [B, Lq, H*64] ready for out_proj. head_dim must be 64 (every BASELINE config). Lq != Lkv is allowed
- * (the 1-query MAP pooling head, image/vit.py:41).
+ * (the 1-query MAP pooling head, image/vit.py:41). flags is reserved (pass 0).
  */
 int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                       long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,

@@ -14,7 +14,6 @@ LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 
 LINEAR_GELU = 1
 LINEAR_DIRECT_STORE = 256
-ATTN_P_SMEM = 1
 DTYPE_BF16 = 0
 DTYPE_F32 = 1
 

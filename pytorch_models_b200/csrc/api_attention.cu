@@ -6,15 +6,11 @@
 using namespace b200;
 
 namespace {
-template <bool kPTmem>
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                      cudaStream_t s) {
-  auto kern = attention_kernel<kPTmem>;
-  constexpr int smem = att_smem_bytes<kPTmem>();
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int max_ctas = 2 * sm_count();
-  const int grid = p.n_items < max_ctas ? p.n_items : max_ctas;
-  kern<<<grid, ATT_THREADS, smem, s>>>(tq, tk, tv, p);
+  B200_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, p);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -43,13 +39,13 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.H = H;
   p.Lq = Lq;
   p.Lkv = Lkv;
-  p.n_qt = (Lq + ATT_BQ - 1) / ATT_BQ;
-  p.n_items = B * H * p.n_qt;
+  p.n_qp = (Lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
+  p.n_items = B * H * p.n_qp;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_batch_stride = out_batch_stride;
   p.ldo = ldo;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (flags & B200ENC_ATTN_P_SMEM) return launch_attention<false>(tq, tk, tv, p, s);
-  return launch_attention<true>(tq, tk, tv, p, s);
+  (void)flags;
+  return launch_attention(tq, tk, tv, p, s);
 }

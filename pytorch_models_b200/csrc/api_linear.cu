@@ -7,25 +7,54 @@ using namespace b200;
 
 namespace {
 
-template <bool kFold, bool kGelu, bool kRes, bool kTma, bool kStats>
+template <int kCtas, bool kFold, bool kGelu, bool kRes, bool kTma, bool kStats>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<kFold, kGelu, kRes, kTma, kStats>;
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, tc, p);
-  B200_CUDA(cudaGetLastError());
+  auto kern = gemm_bf16_kernel<kCtas, kFold, kGelu, kRes, kTma, kStats>;
+  constexpr int kSmem = GemmSmem<kCtas>::kBytes;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return 0;
 }
 
-template <bool kFold, bool kGelu, bool kRes>
+template <int kCtas, bool kFold, bool kGelu, bool kRes>
 int dispatch_store(bool tma, bool stats, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const GemmParams& p, int grid, cudaStream_t s) {
   if constexpr (kRes && !kFold) {
-    if (stats && tma) return launch_gemm<kFold, kGelu, kRes, true, true>(ta, tb, tc, p, grid, s);
+    if (stats && tma) return launch_gemm<kCtas, kFold, kGelu, kRes, true, true>(ta, tb, tc, p, grid, s);
   }
   if (stats) return set_error(-1, "b200enc_linear: stats_out needs a residual, non-folded, TMA-store epilogue");
-  return tma ? launch_gemm<kFold, kGelu, kRes, true, false>(ta, tb, tc, p, grid, s)
-             : launch_gemm<kFold, kGelu, kRes, false, false>(ta, tb, tc, p, grid, s);
+  if constexpr (kCtas == 1) {
+    if (!tma) return launch_gemm<1, kFold, kGelu, kRes, false, false>(ta, tb, tc, p, grid, s);
+  }
+  return launch_gemm<kCtas, kFold, kGelu, kRes, true, false>(ta, tb, tc, p, grid, s);
+}
+
+template <int kCtas>
+int dispatch_epilogue(int sel, bool tma, bool stats, const CUtensorMap& ta, const CUtensorMap& tb,
+                      const CUtensorMap& tc, const GemmParams& p, int grid, cudaStream_t s) {
+  switch (sel) {
+    case 0: return dispatch_store<kCtas, false, false, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 1: return dispatch_store<kCtas, false, false, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 2: return dispatch_store<kCtas, false, true, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 3: return dispatch_store<kCtas, false, true, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 4: return dispatch_store<kCtas, true, false, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 5: return dispatch_store<kCtas, true, false, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 6: return dispatch_store<kCtas, true, true, false>(tma, stats, ta, tb, tc, p, grid, s);
+    default: return dispatch_store<kCtas, true, true, true>(tma, stats, ta, tb, tc, p, grid, s);
+  }
 }
 
 }  // namespace
@@ -58,12 +87,15 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const bool tma_store = (a->flags & B200ENC_LINEAR_DIRECT_STORE) == 0;
   const bool stats = a->stats_out != nullptr;
 
+  // CTA pairs (256-row tiles) unless the problem has at most one 128-row tile per batch or the caller forbids it
+  const bool direct = (a->flags & B200ENC_LINEAR_DIRECT_STORE) != 0;
+  const int ctas = (M > GEMM_BM && !(a->flags & B200ENC_LINEAR_ONE_CTA) && !direct) ? 2 : 1;
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap_bf16(&ta, a->x, K, M, batches, a->ldx, batches > 1 ? a->x_batch_stride : (long long)M * a->ldx,
                            GEMM_BK, GEMM_BM, 128)))
     return rc;
-  if ((rc = make_tmap_bf16(&tb, a->w, K, N, 0, a->ldw, 0, GEMM_BK, GEMM_BN, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tb, a->w, K, N, 0, a->ldw, 0, GEMM_BK, GEMM_BN / ctas, 128))) return rc;
   if ((rc = make_tmap_bf16(&tc, a->out, N, M, batches, a->ldo,
                            batches > 1 ? a->out_batch_stride : (long long)M * a->ldo, 64, 32, 128)))
     return rc;
@@ -77,7 +109,7 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   p.N = N;
   p.K = K;
   p.batches = batches;
-  p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_m = (M + GEMM_BM * ctas - 1) / (GEMM_BM * ctas);
   p.tiles_n = (N + GEMM_BN - 1) / GEMM_BN;
   p.bias = a->bias;
   p.colsum = a->colsum;
@@ -91,20 +123,13 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_batch_stride = a->out_batch_stride;
   p.ldo = a->ldo;
+  p.debug = (a->flags >> 16) & 3;
 
   const long long total = (long long)p.tiles_m * p.tiles_n * batches;
-  const int grid = int(total < sm_count() ? total : sm_count());
+  const int slots = sm_count() / ctas;  // CTAs (or CTA pairs) resident at once: the kernel is persistent
+  const int grid = int(total < slots ? total : slots) * ctas;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-
   const int sel = (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
-  switch (sel) {
-    case 0: return dispatch_store<false, false, false>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 1: return dispatch_store<false, false, true>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 2: return dispatch_store<false, true, false>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 3: return dispatch_store<false, true, true>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 4: return dispatch_store<true, false, false>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 5: return dispatch_store<true, false, true>(tma_store, stats, ta, tb, tc, p, grid, s);
-    case 6: return dispatch_store<true, true, false>(tma_store, stats, ta, tb, tc, p, grid, s);
-    default: return dispatch_store<true, true, true>(tma_store, stats, ta, tb, tc, p, grid, s);
-  }
+  if (ctas == 2) return dispatch_epilogue<2>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
+  return dispatch_epilogue<1>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
 }

@@ -1,14 +1,19 @@
 // Non-causal flash-style attention for head_dim 64 on sm_100a (reference: F.scaled_dot_product_attention call at
 // pytorch_models/transformer.py:52 with attn_mask=None, dropout_p=0, is_causal=False).
 //
-// One work item = (batch, head, 128-query tile). Persistent CTAs loop over items; per item the key/value rows are
-// streamed in blocks of 128 with an online softmax:
-//   warp 0     : TMA producer (Q tile once per item, K/V blocks through a 2-stage ring)
-//   warp 1     : tcgen05.mma issuer:  S = Q K^T (TMEM, fp32)   then   O_blk = P V (P read from TMEM as the A operand)
-//   warps 2..5 : one thread per query row: tcgen05.ld S, running max / sum in registers, exp2 with the softmax scale
-//                folded in, P written back over S as packed bf16, O accumulated in fp32 registers.
+// One work item = (batch, head, pair of 128-row query tiles). One persistent CTA per SM loops over items; key/value
+// rows stream through a 3-stage TMA ring in blocks of 128 with an online softmax. The two query tiles ping-pong so
+// the tensor core works on one tile while the other tile's softmax runs:
+//   warp 0      : TMA producer (Q pair, double-buffered across items; K/V blocks)
+//   warp 1      : tcgen05.mma issuer, order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
+//                   S_t = Q_t K_j^T          -> TMEM, fp32, 128 columns per tile
+//                   O_t[j&1] = P_t V_j       -> TMEM, 64 columns, double-buffered; P_t read from TMEM as the A operand
+//   warps 2..5  : softmax warpgroup of tile 0, warps 6..9 : tile 1. One thread per query row (= TMEM lane):
+//                 two passes of tcgen05.ld over S (row max, then exp2 with the softmax scale folded in), P written
+//                 back over S as packed bf16, running (max, sum) and the fp32 output accumulator in registers;
+//                 the rescale of the accumulator is merged into the FMA that adds the next P.V block.
 // Q/K/V are read straight out of the fused QKV activation [rows, 3d] through strided 3-D tensor maps (no head
-// transpose is materialised), the output is written head-interleaved as [rows, d] for out_proj.
+// transpose is materialised); the output is written head-interleaved as [rows, d] for out_proj.
 #pragma once
 #include "ptx.cuh"
 
@@ -17,40 +22,36 @@ namespace b200 {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
-constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_SMEM_Q = 0;
-constexpr int ATT_SMEM_K = ATT_TILE_BYTES;
+constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
+constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
 constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
-constexpr int ATT_SMEM_P = ATT_SMEM_V + ATT_KV_STAGES * ATT_TILE_BYTES;  // only used by the smem-P variant
-
-template <bool kPTmem>
-constexpr int att_smem_bytes() {
-  return ATT_SMEM_P + (kPTmem ? 0 : 2 * ATT_TILE_BYTES) + 128;
-}
+constexpr int ATT_SMEM_BAR = ATT_SMEM_V + ATT_KV_STAGES * ATT_TILE_BYTES;
+constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 256;
 
 struct AttnParams {
   int B, H, Lq, Lkv;
-  int n_qt;           // ceil(Lq / 128)
-  int n_items;        // B * H * n_qt
+  int n_qp;           // ceil(Lq / 256): query-tile pairs per (batch, head)
+  int n_items;        // B * H * n_qp
   float scale_log2e;  // softmax scale * log2(e)
   __nv_bfloat16* out; // [B, Lq, ldo] with head h at columns [64h, 64h+64)
   long long out_batch_stride;
   int ldo;
 };
 
-template <bool kPTmem>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  constexpr int kBarOff = ATT_SMEM_P + (kPTmem ? 0 : 2 * ATT_TILE_BYTES);
-  const uint32_t bars = sbase + kBarOff;
-  // barrier slots: 0 q_full, 1 q_empty, 2..3 kv_full, 4..5 kv_empty, 6 s_full, 7 p_full, 8 o_full
+  const uint32_t bars = sbase + ATT_SMEM_BAR;
+  // barrier slots: q_full[2] 0..1, q_empty[2] 2..3, kv_full[3] 4..6, kv_empty[3] 7..9,
+  //                s_full[2] 10..11, p_full[2] 12..13, o_full[2] 14..15
   auto bar = [&](int i) { return bars + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 8 * 9);
+  constexpr int Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = 7, S_FULL = 10, P_FULL = 12, O_FULL = 14;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -60,31 +61,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       printf("attention_kernel: dynamic smem base not 1024-aligned (%u)\n", sbase);
       __trap();
     }
-    mbar_init(bar(0), 1);
-    mbar_init(bar(1), 1);
-    for (int s = 0; s < ATT_KV_STAGES; ++s) {
-      mbar_init(bar(2 + s), 1);
-      mbar_init(bar(4 + s), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(Q_FULL + i), 1);
+      mbar_init(bar(Q_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1);
+      mbar_init(bar(P_FULL + i), 4);
+      mbar_init(bar(O_FULL + i), 1);
     }
-    mbar_init(bar(6), 1);
-    mbar_init(bar(7), 4);
-    mbar_init(bar(8), 1);
+    for (int s = 0; s < ATT_KV_STAGES; ++s) {
+      mbar_init(bar(KV_FULL + s), 1);
+      mbar_init(bar(KV_EMPTY + s), 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
   if (warp == 1) {
-    tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 128 fp32 columns; P (bf16 pairs) aliases columns [0, 64)
-  const uint32_t tmem_O = tmem_base + 128;  // 64 fp32 columns
-
+  // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O buffers at t*256 + 128 and t*256 + 192
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 0) {
@@ -92,18 +93,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0, stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qt = item % p.n_qt;
-        const int bh = item / p.n_qt;
+        const int qp = item % p.n_qp;
+        const int bh = item / p.n_qp;
         const int h = bh % p.H;
         const int b = bh / p.H;
-        mbar_wait(bar(1), (it & 1u) ^ 1u);
-        mbar_expect_tx(bar(0), ATT_TILE_BYTES);
-        tma_load_3d(&tmQ, bar(0), sbase + ATT_SMEM_Q, h * ATT_HD, qt * ATT_BQ, b);
+        const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
+        const uint32_t qb = it & 1u;
+        mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar(Q_FULL + qb), (two ? 2 : 1) * ATT_TILE_BYTES);
+        const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
+        tma_load_3d(&tmQ, bar(Q_FULL + qb), sq, h * ATT_HD, qp * 256, b);
+        if (two) tma_load_3d(&tmQ, bar(Q_FULL + qb), sq + ATT_TILE_BYTES, h * ATT_HD, qp * 256 + ATT_BQ, b);
         for (int j = 0; j < n_kvb; ++j) {
-          mbar_wait(bar(4 + stage), phase ^ 1u);
-          mbar_expect_tx(bar(2 + stage), 2 * ATT_TILE_BYTES);
-          tma_load_3d(&tmK, bar(2 + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
-          tma_load_3d(&tmV, bar(2 + stage), sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
+          mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u);
+          mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
+          tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
+          tma_load_3d(&tmV, bar(KV_FULL + stage), sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
           if (++stage == ATT_KV_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -114,147 +119,171 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, stage = 0, phase = 0, gb = 0;
+      uint32_t it = 0, stage = 0, phase = 0;
+      uint32_t g[2] = {0, 0};  // blocks issued so far per tile (barrier parity, O buffer)
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        mbar_wait(bar(0), it & 1u);
-        const uint64_t dq = make_smem_desc_sw128(sbase + ATT_SMEM_Q, 16, 1024);
-        for (int j = 0; j < n_kvb; ++j, ++gb) {
-          const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
-          const int n_mma = (nvalid + 15) & ~15;
-          mbar_wait(bar(2 + stage), phase);
-          tc_fence_after();
-          // S[128 x n_mma] = Q[128 x 64] . K_j[n_mma x 64]^T
-          const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, 16, 1024);
+        const int qp = item % p.n_qp;
+        const bool two = qp * 256 + ATT_BQ < p.Lq;
+        const uint32_t qb = it & 1u;
+        const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
+
+        auto issue_qk = [&](int t, uint32_t st, int n_mma) {
+          const uint64_t dq = make_smem_desc_sw128(sq + t * ATT_TILE_BYTES, 16, 1024);
+          const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + st * ATT_TILE_BYTES, 16, 1024);
           const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma, 0, 0);
 #pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tmem_S, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(bar(6));
-          if (j == n_kvb - 1) umma_commit(bar(1));  // Q tile may be overwritten once these MMAs complete
-          // O_blk[128 x 64] = P[128 x n_mma] . V_j[n_mma x 64]
-          mbar_wait(bar(7), gb & 1u);
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(bar(S_FULL + t));
+        };
+        auto issue_pv = [&](int t, uint32_t st, int n_mma) {
+          mbar_wait(bar(P_FULL + t), g[t] & 1u);
           tc_fence_after();
-          const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
-          const uint32_t sv = sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES;
+          const uint32_t sv = sbase + ATT_SMEM_V + st * ATT_TILE_BYTES;
+          const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
           const int ksteps = n_mma / 16;
           for (int k = 0; k < ksteps; ++k) {
-            // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step
+            // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
             const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
-            if (kPTmem) {
-              umma_ts(tmem_O, tmem_S + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
-            } else {
-              const uint64_t dp =
-                  make_smem_desc_sw128(sbase + ATT_SMEM_P + (k >> 2) * ATT_TILE_BYTES, 16, 1024) + 2u * (k & 3);
-              umma_ss(tmem_O, dp, dv, idesc_o, k != 0 ? 1u : 0u);
-            }
+            umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
           }
-          umma_commit(bar(4 + stage));
-          umma_commit(bar(8));
-          if (++stage == ATT_KV_STAGES) {
-            stage = 0;
-            phase ^= 1u;
+          umma_commit(bar(O_FULL + t));
+          ++g[t];
+        };
+        auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
+
+        mbar_wait(bar(Q_FULL + qb), (it >> 1) & 1u);
+        mbar_wait(bar(KV_FULL + stage), phase);
+        tc_fence_after();
+        issue_qk(0, stage, n_mma_of(0));
+        if (two) issue_qk(1, stage, n_mma_of(0));
+        if (n_kvb == 1) umma_commit(bar(Q_EMPTY + qb));
+        for (int j = 0; j < n_kvb; ++j) {
+          const uint32_t st = stage;
+          uint32_t nst = stage + 1, nphase = phase;
+          if (nst == ATT_KV_STAGES) {
+            nst = 0;
+            nphase ^= 1u;
           }
+          const bool more = j + 1 < n_kvb;
+          issue_pv(0, st, n_mma_of(j));
+          if (more) {
+            mbar_wait(bar(KV_FULL + nst), nphase);
+            tc_fence_after();
+            issue_qk(0, nst, n_mma_of(j + 1));
+          }
+          if (two) {
+            issue_pv(1, st, n_mma_of(j));
+            if (more) issue_qk(1, nst, n_mma_of(j + 1));
+          }
+          umma_commit(bar(KV_EMPTY + st));  // K_j / V_j fully consumed once everything issued so far completes
+          if (more && j + 2 == n_kvb) umma_commit(bar(Q_EMPTY + qb));  // last QK of this item has been issued
+          stage = nst;
+          phase = nphase;
         }
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax / output warps
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
+    // ------------------------------------------------------------ softmax / output warpgroups
+    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int qd = warp & 3;        // TMEM lane quarter
+    const int r = qd * 32 + lane;   // row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + t * 256 + lane_off;
+    const uint32_t tO = tS + 128;
     const float c = p.scale_log2e;
-    uint32_t gb = 0;
+    uint32_t g = 0;  // blocks processed so far by this tile
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qt = item % p.n_qt;
-      const int bh = item / p.n_qt;
+      const int qp = item % p.n_qp;
+      const int bh = item / p.n_qp;
       const int h = bh % p.H;
       const int b = bh / p.H;
-      float m = -INFINITY, l = 0.0f;
+      const int row0 = qp * 256 + t * ATT_BQ;
+      if (row0 >= p.Lq) continue;                         // tile not scheduled at all (mirrors `two` in the MMA warp)
+      const bool warp_live = row0 + qd * 32 < p.Lq;       // any valid row in this warp?
+      const int qrow = row0 + r;
+      float m = -INFINITY, l = 0.0f, alpha_prev = 0.0f;
       float o[ATT_HD];
 #pragma unroll
       for (int i = 0; i < ATT_HD; ++i) o[i] = 0.0f;
 
-      for (int j = 0; j < n_kvb; ++j, ++gb) {
-        const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
-        const int nchunks = (nvalid + 31) >> 5;
-        mbar_wait(bar(6), gb & 1u);
+      auto accumulate_o = [&](uint32_t gprev) {
+        // o = o * alpha(block) + P.V(block), reading the O buffer that block used
+        mbar_wait(bar(O_FULL + t), gprev & 1u);
         tc_fence_after();
-        // pass 1: row maximum
-        float mx = -INFINITY;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + ch * 32, v);
+        if (warp_live) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tO + (gprev & 1u) * 64, v0);
+          tmem_ld32(tO + (gprev & 1u) * 64 + 32, v1);
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float s = (ch * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
-            mx = fmaxf(mx, s);
+            o[i] = fmaf(o[i], alpha_prev, __uint_as_float(v0[i]));
+            o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(v1[i]));
           }
         }
-        const float m_new = fmaxf(m, mx);
-        const float alpha = fast_exp2((m - m_new) * c);
-        const float mc = m_new * c;
-        float lsum = 0.0f;
-        // pass 2: p = exp2(s*c - m*c), row sum, P -> bf16
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + ch * 32, v);
-          tmem_wait_ld();
-          uint32_t pk[16];
+      };
+
+      for (int j = 0; j < n_kvb; ++j, ++g) {
+        const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
+        const int nchunks = (nvalid + 31) >> 5;
+        mbar_wait(bar(S_FULL + t), g & 1u);
+        tc_fence_after();
+        float alpha = 0.0f;
+        if (warp_live) {
+          // pass 1: row maximum over the valid columns
+          float mx = -INFINITY;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(tS + ch * 32, v);
+            tmem_wait_ld();
+            if (ch * 32 + 32 <= nvalid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = ch * 32 + 2 * i;
-            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-            p0 = (col < nvalid) ? p0 : 0.0f;
-            p1 = (col + 1 < nvalid) ? p1 : 0.0f;
-            lsum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          if (kPTmem) {
-            tmem_st16(tmem_S + lane_off + ch * 16, pk);
-          } else {
-            // K-major 128B-swizzled P tile: columns [64t, 64t+64) live in sub-tile t; 16-byte chunk index XOR row%8
-            uint8_t* prow = smem + ATT_SMEM_P + (ch >> 1) * ATT_TILE_BYTES + r * 128;
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            } else {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int chunk16 = (ch & 1) * 4 + q4;
-              *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) =
-                  make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
             }
           }
-        }
-        if (kPTmem) {
+          const float m_new = fmaxf(m, mx);
+          alpha = fast_exp2((m - m_new) * c);
+          const float mc = m_new * c;
+          float lsum = 0.0f;
+          // pass 2: p = exp2(s*c - m*c), row sum, P -> packed bf16 over the S columns
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(tS + ch * 32, v);
+            tmem_wait_ld();
+            uint32_t pk[16];
+            const bool full = ch * 32 + 32 <= nvalid;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+              float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+              if (!full) {
+                p0 = (ch * 32 + 2 * i < nvalid) ? p0 : 0.0f;
+                p1 = (ch * 32 + 2 * i + 1 < nvalid) ? p1 : 0.0f;
+              }
+              lsum += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st16(tS + ch * 16, pk);
+          }
           tmem_wait_st();
-        } else {
-          fence_proxy_async_smem();
+          l = l * alpha + lsum;
+          m = m_new;
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(7));
-        // rescale the running output while the P.V MMA runs
-        l = l * alpha + lsum;
-        m = m_new;
-        if (j > 0) {
-#pragma unroll
-          for (int i = 0; i < ATT_HD; ++i) o[i] *= alpha;
-        }
-        mbar_wait(bar(8), gb & 1u);
-        tc_fence_after();
-        {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_O + lane_off, v0);
-          tmem_ld32(tmem_O + lane_off + 32, v1);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o[i] += __uint_as_float(v0[i]);
-            o[32 + i] += __uint_as_float(v1[i]);
-          }
-        }
-        tc_fence_before();
+        if (lane == 0) mbar_arrive(bar(P_FULL + t));
+        // fold in the previous block's P.V while the tensor core works on this one
+        if (j > 0) accumulate_o(g - 1);
+        alpha_prev = alpha;
       }
+      accumulate_o(g - 1);
+      tc_fence_before();
       // normalise and write the 64 output columns of this head
-      const int qrow = qt * ATT_BQ + r;
       if (qrow < p.Lq) {
         const float inv = 1.0f / l;
         __nv_bfloat16* orow = p.out + (long long)b * p.out_batch_stride + (long long)qrow * p.ldo + h * ATT_HD;
@@ -276,7 +305,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 

@@ -7,6 +7,11 @@
 //                 256-column TMEM accumulators. Two warps per TMEM lane quarter, each owning 128 of the 256
 //                 columns, so every SM sub-partition has two epilogue warps to hide latencies with.
 //
+// kCtas == 2 runs the same roles on a CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x 256 x 16 MMA spans both
+// SMs, each CTA stages only its 128 rows of A and its 128 rows of W, so the L2 -> SM operand traffic per FLOP drops by a
+// third (the 1-CTA tile needs 96 B/clk/SM at full tensor rate, more than the ~64 B/clk an SM can pull from L2) and the
+// same 192 KB of smem holds 6 instead of 4 pipeline stages.
+//
 // This one kernel serves every linear on the encoder path (reference call sites: transformer.py:47-49 fused QKV,
 // transformer.py:53 out_proj, transformer.py:59-67 MLP, vit.py:78 patch embedding as a GEMM over patch rows).
 #pragma once
@@ -17,7 +22,7 @@ namespace b200 {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_STAGES = 4;       // kCtas == 1; the CTA-pair kernel runs GEMM_RING_BYTES / 32 KB = 6 stages
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_STAT_SLICE = 128;  // columns per partial LayerNorm statistic
@@ -25,10 +30,20 @@ constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 32 * 128;  // one staging buffer: 32 rows x 64 bf16
-constexpr int GEMM_SMEM_RING = GEMM_STAGES * GEMM_STAGE_BYTES;
-constexpr int GEMM_SMEM_STG = GEMM_EPI_WARPS * GEMM_STG_BYTES;  // one staging buffer per epilogue warp
 constexpr int GEMM_SMEM_COLVEC = 2 * GEMM_BN * 4;         // bias|c and colsum for one tile
-constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_RING + GEMM_SMEM_STG + GEMM_SMEM_COLVEC + 256;
+// smem plan: kCtas == 1: 4 stages x 48 KB + 1 staging buffer per epilogue warp
+//            kCtas == 2: 5 stages x 32 KB + 2 staging buffers per epilogue warp (store drain never on the critical path)
+template <int kCtas>
+struct GemmSmem {
+  static constexpr int kStages = kCtas == 2 ? 5 : GEMM_STAGES;
+  static constexpr int kBRows = GEMM_BN / kCtas;
+  static constexpr int kStageBytes = GEMM_A_BYTES + kBRows * GEMM_BK * 2;
+  static constexpr int kRing = kStages * kStageBytes;
+  static constexpr int kStgBufs = kCtas == 2 ? 2 : 1;
+  static constexpr int kStg = GEMM_EPI_WARPS * kStgBufs * GEMM_STG_BYTES;
+  static constexpr int kBytes = kRing + kStg + GEMM_SMEM_COLVEC + 256;
+  static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+};
 
 struct GemmParams {
   int M;  // rows per batch
@@ -50,6 +65,7 @@ struct GemmParams {
   __nv_bfloat16* out;          // used by the direct-store path only
   long long out_batch_stride;
   int ldo;
+  int debug;  // timing experiments only: bit0 = skip the output store, bit1 = skip the whole epilogue body
 };
 
 // erf-GELU: x*Phi(x) = relu(x) - |x| * 2^Q(|x|), Q = degree-6 minimax fit of log2(0.5*erfc(t/sqrt2)) on [0,6]
@@ -66,39 +82,45 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-fabsf(x), fast_exp2(q), fmaxf(x, 0.0f));
 }
 
-template <bool kFold, bool kGelu, bool kRes, bool kTmaStore, bool kStats>
+template <int kCtas, bool kFold, bool kGelu, bool kRes, bool kTmaStore, bool kStats>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
+  using SM = GemmSmem<kCtas>;
   const uint32_t ring = smem_base;
-  const uint32_t stg_base = smem_base + GEMM_SMEM_RING;
-  float* colvec = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + GEMM_SMEM_STG);
-  const uint32_t bars = smem_base + GEMM_SMEM_RING + GEMM_SMEM_STG + GEMM_SMEM_COLVEC;
-  // barrier slots (8 bytes each): full[4] empty[4] tfull[2] tempty[2]; then the TMEM base address word.
+  float* colvec = reinterpret_cast<float*>(smem + SM::kRing + SM::kStg);
+  const uint32_t bars = smem_base + SM::kRing + SM::kStg + GEMM_SMEM_COLVEC;
+  // Per-CTA geometry: with kCtas == 2 this CTA stages 128 rows of A and 128 (of the tile's 256) rows of W per stage.
+  constexpr int kStages = SM::kStages;
+  constexpr int kBRows = SM::kBRows;
+  constexpr int kStageBytes = SM::kStageBytes;
+  constexpr int kTileM = GEMM_BM * kCtas;
+  // barrier slots (8 bytes each): full[kStages] empty[kStages] tfull[2] tempty[2]; then the TMEM base address word.
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (GEMM_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * GEMM_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * GEMM_STAGES + 2 + a); };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
-      smem + GEMM_SMEM_RING + GEMM_SMEM_STG + GEMM_SMEM_COLVEC + 8 * (2 * GEMM_STAGES + 4));
+      smem + SM::kRing + SM::kStg + GEMM_SMEM_COLVEC + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
 
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) {
       printf("gemm_bf16_kernel: dynamic smem base not 1024-aligned (%u)\n", smem_base);
       __trap();
     }
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // the leader's producer arrives (expect_tx covers both CTAs' bytes)
+      mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when kCtas == 2)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), GEMM_EPI_WARPS);
+      mbar_init(tempty_bar(a), GEMM_EPI_WARPS * kCtas);  // both CTAs' epilogue warps release the leader's MMA warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -106,34 +128,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (kTmaStore) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
-    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-    tmem_relinquish();
+    if (kCtas == 2) {
+      tmem_alloc_2cta<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batches;
+  const int first_tile = blockIdx.x / kCtas;  // both CTAs of a pair walk the same tile sequence
+  const int tile_step = gridDim.x / kCtas;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
-        const int m0 = (r / p.tiles_n) * GEMM_BM;
-        const int n0 = (r % p.tiles_n) * GEMM_BN;
+        const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;
+        const int n0 = (r % p.tiles_n) * GEMM_BN + int(cta_rank) * kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), GEMM_STAGE_BYTES);
-          const uint32_t sa = ring + stage * GEMM_STAGE_BYTES;
-          tma_load_3d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0, b);
-          tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
-          if (++stage == GEMM_STAGES) {
+          const uint32_t sa = ring + stage * kStageBytes;
+          if (kCtas == 2) {
+            // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
+            const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+            tma_load_3d_2cta(&tmA, leader_full, sa, kb * GEMM_BK, m0, b);
+            tma_load_2d_2cta(&tmB, leader_full, sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), kStageBytes);
+            tma_load_3d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0, b);
+            tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
+          }
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -141,32 +178,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, GEMM_BN, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = ring + stage * GEMM_STAGE_BYTES;
+          const uint32_t sa = ring + stage * kStageBytes;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kCtas == 2)
+              umma_ss_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
-          if (++stage == GEMM_STAGES) {
+          if (kCtas == 2) umma_commit_2cta(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
+        if (kCtas == 2) umma_commit_2cta(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -176,16 +216,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int hf = (warp - 2) >> 2;        // which 128-column half of the tile this warp owns
     const int e = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
-    const uint32_t stg = stg_base + (warp - 2) * GEMM_STG_BYTES;
-    uint8_t* stg_ptr = smem + GEMM_SMEM_RING + (warp - 2) * GEMM_STG_BYTES;
+    const uint32_t stg = smem_base + SM::kRing + (warp - 2) * (SM::kStgBufs * GEMM_STG_BYTES);
+    uint8_t* stg_ptr = smem + SM::kRing + (warp - 2) * (SM::kStgBufs * GEMM_STG_BYTES);
     float* cv_b = colvec;
     float* cv_s = colvec + GEMM_BN;
     const int n_slices = (p.N + GEMM_STAT_SLICE - 1) / GEMM_STAT_SLICE;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tempty_leader0 = kCtas == 2 ? map_to_cta(tempty_bar(0), 0) : tempty_bar(0);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
-      const int m0 = (r / p.tiles_n) * GEMM_BM;
+      const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;  // first row owned by this CTA
       const int n0 = (r % p.tiles_n) * GEMM_BN;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
@@ -252,6 +293,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       float st_shift = 0.0f, st_s1 = 0.0f, st_s2 = 0.0f;
+      bool released = false;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -260,11 +302,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int nc = nh + cc * 64;
-        if (nc >= p.N) break;
+        if (nc >= p.N || (p.debug & 2)) break;
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr + cc * 64, v0);
         tmem_ld32(taddr + cc * 64 + 32, v1);
         tmem_wait_ld();
+        if (cc == 1 || nc + 64 >= p.N) {
+          // last TMEM read of this accumulator by this warp: hand it back to the MMA warp before doing the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCtas == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+          }
+          released = true;
+        }
 
         uint32_t packed[32];
 #pragma unroll
@@ -307,10 +358,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
 
+        if (p.debug & 1) continue;
         if (kTmaStore) {
-          if (lane == 0) tma_store_wait_read<0>();  // the previous store out of this buffer has drained
+          // with two buffers the store that last used this one was issued a whole tile ago: no drain on the critical path
+          constexpr int kBufOff = SM::kStgBufs == 2 ? GEMM_STG_BYTES : 0;
+          if (lane == 0) tma_store_wait_read<SM::kStgBufs - 1>();
           __syncwarp();
-          uint8_t* dst = stg_ptr + lane * 128;
+          uint8_t* dst = stg_ptr + cc * kBufOff + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) =
@@ -319,7 +373,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmC, stg, nc, m0 + q * 32, b);
+            tma_store_3d(&tmC, stg + cc * kBufOff, nc, m0 + q * 32, b);
             tma_store_commit();
           }
         } else {
@@ -340,10 +394,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float m2_t = fmaxf(st_s2 - st_s1 * st_s1 / nt, 0.0f);
         p.stats_out[((long long)b * p.M + row) * n_slices + nh / GEMM_STAT_SLICE] = make_float2(mean_t, m2_t);
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (!released) {  // warp owned no valid columns in this tile (N tail) or the epilogue body was skipped
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc); else mbar_arrive(tempty_bar(acc));
+        }
+      }
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -351,11 +408,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();  // the peer may still arrive on / read from this CTA's smem
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kCtas == 2) tmem_dealloc_2cta<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
 }
 

@@ -145,7 +145,8 @@ static bool run_linear(const LinearCase& c) {
   CK(cudaMemcpy(dr.p, hr.data(), hr.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));  // sentinel 0x7f7f = 3.39e38 in bf16
 
-  const int flags = (c.gelu ? B200ENC_LINEAR_GELU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0);
+  const int dbg = getenv("B200_DEBUG_FLAGS") ? atoi(getenv("B200_DEBUG_FLAGS")) : 0;  // timing experiments only
+  const int flags = (c.gelu ? B200ENC_LINEAR_GELU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
   const int n_slices = (N + 127) / 128;
   const bool want_stats = c.res && !c.fold && !c.direct;
   DevBuf dso(size_t(B) * M * n_slices * 8);
@@ -233,18 +234,19 @@ static bool run_linear(const LinearCase& c) {
     ok = report("fused_stats", ss) && ok;
   }
 
-  if (ok && c.time_iters > 0) {
+  if ((ok || dbg) && c.time_iters > 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    const int iters = getenv("B200_ITERS") ? atoi(getenv("B200_ITERS")) : c.time_iters;
     for (int i = 0; i < 3; ++i) call();
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < c.time_iters; ++i) call();
+    for (int i = 0; i < iters; ++i) call();
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    ms /= c.time_iters;
+    ms /= iters;
     const double fl = 2.0 * B * double(M) * N * K;
     printf("  time %s: %.3f ms  %.1f TFLOP/s\n", c.name, ms, fl / ms * 1e-9);
     fflush(stdout);
@@ -271,6 +273,10 @@ static const LinearCase kLinearCases[] = {
     {"perf_fc1", 1, 25216, 3072, 768, true, true, false, false, false, false, 0, 16, 20},
     {"perf_fc2", 1, 25216, 768, 3072, false, false, true, false, false, false, 0, 16, 20},
     {"perf_qkv_direct", 1, 25216, 2304, 768, true, false, false, false, true, false, 0, 16, 20},
+    {"perf_qkv_l2fit", 1, 8192, 2304, 768, true, false, false, false, false, false, 0, 16, 60},
+    {"perf_qkv_big", 1, 201728, 2304, 768, true, false, false, false, false, false, 0, 8, 10},
+    {"perf_fc1_big", 1, 201728, 3072, 768, true, true, false, false, false, false, 0, 8, 10},
+    {"perf_k4096", 1, 25216, 2304, 4096, false, false, false, false, false, false, 0, 8, 10},
 };
 
 
@@ -316,7 +322,7 @@ static bool run_attn(const AttnCase& c) {
   auto call = [&]() {
     return b200enc_attention(dq.p, (long long)Lq * ldq, ldq, kvbase_d + koff, kvbase_d + voff, (long long)Lkv * ldkv,
                              ldkv, dout.p, (long long)Lq * D, D, B, H, Lq, Lkv, 64, scale,
-                             c.p_smem ? B200ENC_ATTN_P_SMEM : 0, nullptr);
+                             0, nullptr);
   };
   int rc = call();
   if (rc) {

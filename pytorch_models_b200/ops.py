@@ -123,7 +123,7 @@ def linear(
     return out
 
 
-def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, *, p_smem: bool = False) -> Tensor:
+def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float) -> Tensor:
     """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64)."""
     _need_cuda(q, k, v, out)
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -140,7 +140,7 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
         "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv),
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),
         out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
-        _lib.ATTN_P_SMEM if p_smem else 0, _stream(),
+        0, _stream(),
     )
     return out
 
