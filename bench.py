@@ -311,6 +311,7 @@ def main() -> None:
             torch.cuda.synchronize()
             ops.profile(False)
         by_kernel: dict[str, list[float]] = {}
+        by_shape: dict[str, list[float]] = {}
         gemm_ms = gemm_flops = 0.0
         for name, meta, a, b in rec:
             ms = a.elapsed_time(b)
@@ -318,8 +319,14 @@ def main() -> None:
             by_kernel[name][0] += ms
             by_kernel[name][1] += 1
             if name == "b200enc_linear":
+                fl = 2.0 * meta["batches"] * meta["M"] * meta["N"] * meta["K"]
                 gemm_ms += ms
-                gemm_flops += 2.0 * meta["batches"] * meta["M"] * meta["N"] * meta["K"]
+                gemm_flops += fl
+                key = f"N{meta['N']}_K{meta['K']}" + ("_ln" if meta["fold"] else "") + ("_gelu" if meta["gelu"] else "") + ("_res" if meta["res"] else "")
+                acc = by_shape.setdefault(key, [0.0, 0.0, 0])
+                acc[0] += ms
+                acc[1] += fl
+                acc[2] += 1
         peaks = measured_peaks()
         total_ms = sum(v[0] for v in by_kernel.values())
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
@@ -330,6 +337,8 @@ def main() -> None:
             "frac_of_burst": achieved / peaks["burst"], "traffic": None,
             "launches_per_step": by_kernel["b200enc_linear"][1], "avg_launch_ms": gemm_ms / by_kernel["b200enc_linear"][1],
             "share_of_step": gemm_ms / total_ms,
+            "by_shape": {k: {"launches": v[2], "avg_ms": round(v[0] / v[2], 4), "tflops": round(v[1] / v[0] * 1e-9, 1)}
+                         for k, v in by_shape.items()},
             "step_breakdown_ms": {k: round(v[0], 3) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
         }
 

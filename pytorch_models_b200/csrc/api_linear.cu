@@ -76,6 +76,8 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
     B200_CHECK_ARG(a->rowstats_parts == 0 || (a->rowstats_parts == want && want <= 12),
                    "b200enc_linear: rowstats_parts=%d must be 0 or ceil(K/128)=%d (<= 12)", a->rowstats_parts, want);
   }
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a->colsum) & 15u) == 0,
+                 "b200enc_linear: bias / colsum must be 16-byte aligned");
   if (a->residual) {
     B200_CHECK_ARG(a->ldr >= N && a->ldr % 8 == 0 && a->res_batch_stride % 8 == 0 &&
                        (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0,

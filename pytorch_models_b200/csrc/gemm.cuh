@@ -22,24 +22,26 @@ namespace b200 {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;       // kCtas == 1; the CTA-pair kernel runs GEMM_RING_BYTES / 32 KB = 6 stages
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
+#ifndef GEMM_STAGES_2CTA
+#define GEMM_STAGES_2CTA 5
+#endif
 constexpr int GEMM_STAT_SLICE = 128;  // columns per partial LayerNorm statistic
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 32 * 128;  // one staging buffer: 32 rows x 64 bf16
-constexpr int GEMM_SMEM_COLVEC = 2 * GEMM_BN * 4;         // bias|c and colsum for one tile
-// smem plan: kCtas == 1: 4 stages x 48 KB + 1 staging buffer per epilogue warp
-//            kCtas == 2: 5 stages x 32 KB + 2 staging buffers per epilogue warp (store drain never on the critical path)
+constexpr int GEMM_SMEM_COLVEC = GEMM_EPI_WARPS * 2 * 128 * 4;  // per warp: bias|c and colsum of its 128 columns
+// smem plan: kCtas == 1: 3 stages x 48 KB + 1 staging buffer per epilogue warp (only used for problems of <= 128 rows)
+//            kCtas == 2: 4 stages x 32 KB + 2 staging buffers per epilogue warp (store drain never on the critical path)
 template <int kCtas>
 struct GemmSmem {
-  static constexpr int kStages = kCtas == 2 ? 5 : GEMM_STAGES;
+  static constexpr int kStages = kCtas == 2 ? GEMM_STAGES_2CTA : 3;
   static constexpr int kBRows = GEMM_BN / kCtas;
   static constexpr int kStageBytes = GEMM_A_BYTES + kBRows * GEMM_BK * 2;
   static constexpr int kRing = kStages * kStageBytes;
-  static constexpr int kStgBufs = kCtas == 2 ? 2 : 1;
+  static constexpr int kStgBufs = (kCtas == 2 && GEMM_STAGES_2CTA <= 4) ? 2 : 1;
   static constexpr int kStg = GEMM_EPI_WARPS * kStgBufs * GEMM_STG_BYTES;
   static constexpr int kBytes = kRing + kStg + GEMM_SMEM_COLVEC + 256;
   static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -70,16 +72,19 @@ struct GemmParams {
 
 // erf-GELU: x*Phi(x) = relu(x) - |x| * 2^Q(|x|), Q = degree-6 minimax fit of log2(0.5*erfc(t/sqrt2)) on [0,6]
 // (max abs error 2.8e-7 vs the exact erf form, measured in fp32; reference op: nn.GELU(), transformer.py:61).
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float t = fminf(fabsf(x), 6.0f);
-  float q = 3.310347528895363e-05f;
-  q = fmaf(q, t, -0.0007693132502026856f);
-  q = fmaf(q, t, 0.008081023581326008f);
-  q = fmaf(q, t, -0.053412578999996185f);
-  q = fmaf(q, t, -0.45877063274383545f);
-  q = fmaf(q, t, -1.151201844215393f);
-  q = fmaf(q, t, -0.9999930262565613f);
-  return fmaf(-fabsf(x), fast_exp2(q), fmaxf(x, 0.0f));
+// Evaluated on two columns at once with the packed fp32 pipe (FFMA2): s = -min(|x|, 6), Horner in s (odd
+// coefficients negated), one MUFU.EX2 per element, result = s * 2^Q + relu(x)  (for |x| > 6 the factor is < 1e-9).
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 s = make_float2(fmaxf(-fabsf(x.x), -6.0f), fmaxf(-fabsf(x.y), -6.0f));
+  float2 q = make_float2(3.310347528895363e-05f, 3.310347528895363e-05f);
+  q = __ffma2_rn(q, s, make_float2(0.0007693132502026856f, 0.0007693132502026856f));
+  q = __ffma2_rn(q, s, make_float2(0.008081023581326008f, 0.008081023581326008f));
+  q = __ffma2_rn(q, s, make_float2(0.053412578999996185f, 0.053412578999996185f));
+  q = __ffma2_rn(q, s, make_float2(-0.45877063274383545f, -0.45877063274383545f));
+  q = __ffma2_rn(q, s, make_float2(1.151201844215393f, 1.151201844215393f));
+  q = __ffma2_rn(q, s, make_float2(-0.9999930262565613f, -0.9999930262565613f));
+  const float2 e = make_float2(fast_exp2(q.x), fast_exp2(q.y));
+  return __ffma2_rn(s, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
 template <int kCtas, bool kFold, bool kGelu, bool kRes, bool kTmaStore, bool kStats>
@@ -215,11 +220,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int hf = (warp - 2) >> 2;        // which 128-column half of the tile this warp owns
-    const int e = (warp - 2) * 32 + lane;  // 0..255 among epilogue threads
     const uint32_t stg = smem_base + SM::kRing + (warp - 2) * (SM::kStgBufs * GEMM_STG_BYTES);
     uint8_t* stg_ptr = smem + SM::kRing + (warp - 2) * (SM::kStgBufs * GEMM_STG_BYTES);
-    float* cv_b = colvec;
-    float* cv_s = colvec + GEMM_BN;
+    float* cv_b = colvec + (warp - 2) * 256;  // this warp's private copy of bias|c for its 128 columns ...
+    float* cv_s = cv_b + 128;                 // ... and of the LayerNorm-fold column sums
     const int n_slices = (p.N + GEMM_STAT_SLICE - 1) / GEMM_STAT_SLICE;
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t tempty_leader0 = kCtas == 2 ? map_to_cta(tempty_bar(0), 0) : tempty_bar(0);
@@ -233,10 +237,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nh = n0 + hf * 128;  // first column owned by this warp
 
       // ---- issue every global load of this tile up front: they complete while the tile's main loop still runs
-      float my_b = 0.0f, my_s = 0.0f;
-      if (n0 + e < p.N) {
-        if (p.bias != nullptr) my_b = __ldg(p.bias + n0 + e);
-        if (kFold) my_s = __ldg(p.colsum + n0 + e);
+      float4 my_b = make_float4(0.f, 0.f, 0.f, 0.f), my_s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nh + 4 * lane < p.N) {  // N is a multiple of 8: the 4 columns of a lane are all valid or all out of range
+        if (p.bias != nullptr) my_b = __ldg(reinterpret_cast<const float4*>(p.bias + nh) + lane);
+        if (kFold) my_s = __ldg(reinterpret_cast<const float4*>(p.colsum + nh) + lane);
       }
       float2 st_full = make_float2(0.0f, 1.0f);
       constexpr int kMaxParts = 12;
@@ -264,10 +268,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
       }
 
-      named_bar_sync(1, 32 * GEMM_EPI_WARPS);  // everyone finished reading the previous tile's column vectors
-      cv_b[e] = my_b;
-      if (kFold) cv_s[e] = my_s;
-      named_bar_sync(1, 32 * GEMM_EPI_WARPS);
+      __syncwarp();  // every lane finished reading the previous tile's column vectors
+      reinterpret_cast<float4*>(cv_b)[lane] = my_b;
+      if (kFold) reinterpret_cast<float4*>(cv_s)[lane] = my_s;
+      __syncwarp();
 
       float rstd = 1.0f, nmr = 0.0f;  // nmr = -mean * rstd
       if (kFold) {
@@ -292,7 +296,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           nmr = -mean * rstd;
         }
       }
-      float st_shift = 0.0f, st_s1 = 0.0f, st_s2 = 0.0f;
+      float st_shift = 0.0f;
+      float2 st_s1 = make_float2(0.f, 0.f), st_s2 = make_float2(0.f, 0.f);
       bool released = false;
 
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -318,42 +323,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
 
         uint32_t packed[32];
+        const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
 #pragma unroll
         for (int j4 = 0; j4 < 16; ++j4) {
-          // 4 columns per step: column vectors come from smem as one broadcast 16-byte load each
-          const float4 cb = *reinterpret_cast<const float4*>(cv_b + hf * 128 + cc * 64 + 4 * j4);
+          // 4 columns per step as two fp32 pairs (packed FFMA2 pipe); column vectors are broadcast 16-byte smem loads
+          const float4 cb = *reinterpret_cast<const float4*>(cv_b + cc * 64 + 4 * j4);
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kFold) cs = *reinterpret_cast<const float4*>(cv_s + hf * 128 + cc * 64 + 4 * j4);
-          float x[4];
-          const float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
-          const float csv[4] = {cs.x, cs.y, cs.z, cs.w};
+          if (kFold) cs = *reinterpret_cast<const float4*>(cv_s + cc * 64 + 4 * j4);
+          float2 x[2];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = 4 * j4 + u;
-            const float a = __uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]);
-            x[u] = kFold ? fmaf(rstd, a, fmaf(nmr, csv[u], cbv[u])) : a + cbv[u];
-            if (kGelu) x[u] = gelu_erf_fast(x[u]);
+          for (int u = 0; u < 2; ++u) {
+            const int idx = 4 * j4 + 2 * u;
+            const float2 a = make_float2(__uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]),
+                                         __uint_as_float(idx < 32 ? v0[idx + 1] : v1[idx + 1 - 32]));
+            const float2 cb2 = u == 0 ? make_float2(cb.x, cb.y) : make_float2(cb.z, cb.w);
+            const float2 cs2 = u == 0 ? make_float2(cs.x, cs.y) : make_float2(cs.z, cs.w);
+            x[u] = kFold ? __ffma2_rn(rstd2, a, __ffma2_rn(nmr2, cs2, cb2)) : __fadd2_rn(a, cb2);
+            if (kGelu) x[u] = gelu_erf_fast2(x[u]);
+            if (kRes) {
+              const uint32_t rr = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + u];
+              x[u] = __fadd2_rn(x[u], make_float2(bf16_lo(rr), bf16_hi(rr)));
+            }
+            packed[2 * j4 + u] = pack_bf16x2(x[u].x, x[u].y);
           }
-          if (kRes) {
-            const uint32_t r0 = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4];
-            const uint32_t r1 = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + 1];
-            x[0] += bf16_lo(r0);
-            x[1] += bf16_hi(r0);
-            x[2] += bf16_lo(r1);
-            x[3] += bf16_hi(r1);
-          }
-          packed[2 * j4] = pack_bf16x2(x[0], x[1]);
-          packed[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
           if (kStats) {
             // statistics of the values as stored (bf16-rounded), shifted by the row's first value in this slice
-            const float y[4] = {bf16_lo(packed[2 * j4]), bf16_hi(packed[2 * j4]), bf16_lo(packed[2 * j4 + 1]),
-                                bf16_hi(packed[2 * j4 + 1])};
-            if (cc == 0 && j4 == 0) st_shift = y[0];
+            if (cc == 0 && j4 == 0) st_shift = bf16_lo(packed[0]);
+            const float2 sh2 = make_float2(-st_shift, -st_shift);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float dlt = (nc + 4 * j4 + u < p.N) ? y[u] - st_shift : 0.0f;
-              st_s1 += dlt;
-              st_s2 = fmaf(dlt, dlt, st_s2);
+            for (int u = 0; u < 2; ++u) {
+              float2 dlt = __fadd2_rn(make_float2(bf16_lo(packed[2 * j4 + u]), bf16_hi(packed[2 * j4 + u])), sh2);
+              if (nc + 4 * j4 + 2 * u + 1 >= p.N) {  // only possible in the last, partial chunk of the matrix
+                if (nc + 4 * j4 + 2 * u >= p.N) dlt.x = 0.0f;
+                dlt.y = 0.0f;
+              }
+              st_s1 = __fadd2_rn(st_s1, dlt);
+              st_s2 = __ffma2_rn(dlt, dlt, st_s2);
             }
           }
         }
@@ -390,8 +395,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (kStats && row_ok && nh < p.N) {
         const float nt = float(min(GEMM_STAT_SLICE, p.N - nh));
-        const float mean_t = st_shift + st_s1 / nt;
-        const float m2_t = fmaxf(st_s2 - st_s1 * st_s1 / nt, 0.0f);
+        const float s1 = st_s1.x + st_s1.y, s2 = st_s2.x + st_s2.y;
+        const float mean_t = st_shift + s1 / nt;
+        const float m2_t = fmaxf(s2 - s1 * s1 / nt, 0.0f);
         p.stats_out[((long long)b * p.M + row) * n_slices + nh / GEMM_STAT_SLICE] = make_float2(mean_t, m2_t);
       }
       if (!released) {  // warp owned no valid columns in this tile (N tail) or the epilogue body was skipped
