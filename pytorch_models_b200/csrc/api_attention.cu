@@ -5,6 +5,12 @@
 
 using namespace b200;
 
+#ifdef ATT_TRACE
+// debug builds only (scripts/gpu_trace_attention.sh): event trace buffer of CTA 0, see ATT_EV in attention.cuh
+static long long* g_attention_trace = nullptr;
+extern "C" void b200enc_debug_attention_trace(long long* buf) { g_attention_trace = buf; }
+#endif
+
 namespace {
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                      cudaStream_t s) {
@@ -45,6 +51,11 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_batch_stride = out_batch_stride;
   p.ldo = ldo;
+#ifdef ATT_TRACE
+  p.trace = g_attention_trace;
+#else
+  p.trace = nullptr;
+#endif
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   (void)flags;
   return launch_attention(tq, tk, tv, p, s);

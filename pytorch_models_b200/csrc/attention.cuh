@@ -25,6 +25,9 @@ constexpr int ATT_HD = 64;
 constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int ATT_KV_STAGES = 3;
+#ifndef ATT_PIPELINED_LD
+#define ATT_PIPELINED_LD 0
+#endif
 constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
 constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
 constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
@@ -39,7 +42,22 @@ struct AttnParams {
   __nv_bfloat16* out; // [B, Lq, ldo] with head h at columns [64h, 64h+64)
   long long out_batch_stride;
   int ldo;
+  long long* trace;   // debug only: (event, clock) records of CTA 0 (nullptr in production)
 };
+
+#ifdef ATT_TRACE
+// per-role private trace slots (no atomics: a store and a clock read per event)
+#define ATT_EV(ev)                                                              \
+  do {                                                                          \
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < 1000) {                 \
+      p.trace[2 * (tr_role * 1000 + tr_n)] = (ev);                              \
+      p.trace[2 * (tr_role * 1000 + tr_n) + 1] = clock64();                     \
+      ++tr_n;                                                                   \
+    }                                                                           \
+  } while (0)
+#else
+#define ATT_EV(ev) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -55,6 +73,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef ATT_TRACE
+  int tr_n = 0;
+  const int tr_role = warp == 0 ? 0 : warp == 1 ? 1 : warp < 6 ? 2 : 3;
+#endif
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {
@@ -104,11 +126,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
         tma_load_3d(&tmQ, bar(Q_FULL + qb), sq, h * ATT_HD, qp * 256, b);
         if (two) tma_load_3d(&tmQ, bar(Q_FULL + qb), sq + ATT_TILE_BYTES, h * ATT_HD, qp * 256 + ATT_BQ, b);
+        ATT_EV(10);
         for (int j = 0; j < n_kvb; ++j) {
           mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u);
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
           tma_load_3d(&tmV, bar(KV_FULL + stage), sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
+          ATT_EV(11);
           if (++stage == ATT_KV_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -119,68 +143,86 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, stage = 0, phase = 0;
+      // The (item, kv-block) sequence of this CTA is walked as ONE stream: while block `cur` is being finished
+      // (PV0, PV1) the score MMAs of the following block `nxt` — possibly the first block of the next item — are
+      // already issued, so a tile's softmax never waits for the other tile's tail.
       uint32_t g[2] = {0, 0};  // blocks issued so far per tile (barrier parity, O buffer)
       const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qp = item % p.n_qp;
-        const bool two = qp * 256 + ATT_BQ < p.Lq;
-        const uint32_t qb = it & 1u;
-        const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
-
-        auto issue_qk = [&](int t, uint32_t st, int n_mma) {
-          const uint64_t dq = make_smem_desc_sw128(sq + t * ATT_TILE_BYTES, 16, 1024);
-          const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + st * ATT_TILE_BYTES, 16, 1024);
-          const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma, 0, 0);
+      struct Blk {
+        int item, j;
+        uint32_t it, stage, phase;
+        bool two;
+      };
+      auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
+      auto is_two = [&](int item) { return (item % p.n_qp) * 256 + ATT_BQ < p.Lq; };
+      auto issue_qk = [&](const Blk& bl, int t) {
+        const uint32_t sq = sbase + ATT_SMEM_Q + (bl.it & 1u) * 2 * ATT_TILE_BYTES + t * ATT_TILE_BYTES;
+        const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
+        const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + bl.stage * ATT_TILE_BYTES, 16, 1024);
+        const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma_of(bl.j), 0, 0);
 #pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(bar(S_FULL + t));
-        };
-        auto issue_pv = [&](int t, uint32_t st, int n_mma) {
-          mbar_wait(bar(P_FULL + t), g[t] & 1u);
-          tc_fence_after();
-          const uint32_t sv = sbase + ATT_SMEM_V + st * ATT_TILE_BYTES;
-          const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
-          const int ksteps = n_mma / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
-            const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
-            umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
-          }
-          umma_commit(bar(O_FULL + t));
-          ++g[t];
-        };
-        auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
-
-        mbar_wait(bar(Q_FULL + qb), (it >> 1) & 1u);
-        mbar_wait(bar(KV_FULL + stage), phase);
+        for (int k = 0; k < ATT_HD / 16; ++k)
+          umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(bar(S_FULL + t));
+        ATT_EV(100 + t);
+      };
+      auto issue_pv = [&](const Blk& bl, int t) {
+        mbar_wait(bar(P_FULL + t), g[t] & 1u);
+        ATT_EV(110 + t);
         tc_fence_after();
-        issue_qk(0, stage, n_mma_of(0));
-        if (two) issue_qk(1, stage, n_mma_of(0));
-        if (n_kvb == 1) umma_commit(bar(Q_EMPTY + qb));
-        for (int j = 0; j < n_kvb; ++j) {
-          const uint32_t st = stage;
-          uint32_t nst = stage + 1, nphase = phase;
-          if (nst == ATT_KV_STAGES) {
-            nst = 0;
-            nphase ^= 1u;
-          }
-          const bool more = j + 1 < n_kvb;
-          issue_pv(0, st, n_mma_of(j));
-          if (more) {
-            mbar_wait(bar(KV_FULL + nst), nphase);
-            tc_fence_after();
-            issue_qk(0, nst, n_mma_of(j + 1));
-          }
-          if (two) {
-            issue_pv(1, st, n_mma_of(j));
-            if (more) issue_qk(1, nst, n_mma_of(j + 1));
-          }
-          umma_commit(bar(KV_EMPTY + st));  // K_j / V_j fully consumed once everything issued so far completes
-          if (more && j + 2 == n_kvb) umma_commit(bar(Q_EMPTY + qb));  // last QK of this item has been issued
-          stage = nst;
-          phase = nphase;
+        const uint32_t sv = sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES;
+        const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
+        const int ksteps = n_mma_of(bl.j) / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
+          const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
+          umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(O_FULL + t));
+        ATT_EV(120 + t);
+        ++g[t];
+      };
+      // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
+      auto start_block = [&](const Blk& bl, int t_first, int t_last) {
+        if (t_first == 0) {
+          if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u);
+          mbar_wait(bar(KV_FULL + bl.stage), bl.phase);
+          ATT_EV(130);
+          tc_fence_after();
+        }
+        for (int t = t_first; t <= t_last; ++t)
+          if (t == 0 || bl.two) issue_qk(bl, t);
+        // after the last score MMA that reads this item's Q tiles has been issued, hand the Q buffer back
+        if (t_last == 1 && bl.j == n_kvb - 1) umma_commit(bar(Q_EMPTY + (bl.it & 1u)));
+      };
+      auto advance = [&](Blk bl) {
+        if (++bl.stage == ATT_KV_STAGES) {
+          bl.stage = 0;
+          bl.phase ^= 1u;
+        }
+        if (++bl.j == n_kvb) {
+          bl.j = 0;
+          bl.item += gridDim.x;
+          ++bl.it;
+          bl.two = bl.item < p.n_items ? is_two(bl.item) : false;
+        }
+        return bl;
+      };
+
+      Blk cur{int(blockIdx.x), 0, 0u, 0u, 0u, false};
+      if (cur.item < p.n_items) {
+        cur.two = is_two(cur.item);
+        start_block(cur, 0, 1);
+        while (true) {
+          const Blk nxt = advance(cur);
+          const bool more = nxt.item < p.n_items;
+          issue_pv(cur, 0);
+          if (more) start_block(nxt, 0, 0);
+          if (cur.two) issue_pv(cur, 1);
+          if (more) start_block(nxt, 1, 1);
+          umma_commit(bar(KV_EMPTY + cur.stage));  // K/V of `cur` are free once everything issued so far completes
+          if (!more) break;
+          cur = nxt;
         }
       }
     }
@@ -209,9 +251,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int i = 0; i < ATT_HD; ++i) o[i] = 0.0f;
 
       auto accumulate_o = [&](uint32_t gprev) {
-        // o = o * alpha(block) + P.V(block), reading the O buffer that block used
-        mbar_wait(bar(O_FULL + t), gprev & 1u);
-        tc_fence_after();
+        // o = o * alpha(block) + P.V(block), reading the O buffer that block used (its O_FULL was already awaited)
         if (warp_live) {
           uint32_t v0[32], v1[32];
           tmem_ld32(tO + (gprev & 1u) * 64, v0);
@@ -229,8 +269,68 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
         const int nchunks = (nvalid + 31) >> 5;
         mbar_wait(bar(S_FULL + t), g & 1u);
+        if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
         float alpha = 0.0f;
+#if ATT_PIPELINED_LD
+        if (warp_live) {
+          // Both passes keep one tcgen05.ld in flight while the previous 32 columns are processed.
+          uint32_t v[2][32];
+          // pass 1: row maximum over the valid columns
+          float mx = -INFINITY;
+          tmem_ld32(tS, v[0]);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            if (ch < nchunks) {
+              tmem_wait_ld();
+              if (ch + 1 < nchunks) tmem_ld32(tS + (ch + 1) * 32, v[(ch + 1) & 1]);
+              else tmem_ld32(tS, v[(ch + 1) & 1]);  // first chunk of pass 2
+              if (ch * 32 + 32 <= nvalid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[ch & 1][i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(v[ch & 1][i]) : -INFINITY);
+              }
+            }
+          }
+          const float m_new = fmaxf(m, mx);
+          alpha = fast_exp2((m - m_new) * c);
+          const float mc = m_new * c;
+          float lsum = 0.0f;
+          // pass 2: p = exp2(s*c - m*c), row sum, P -> packed bf16 over the S columns. Chunk ch of pass 2 sits in
+          // buffer (nchunks + ch) & 1 because pass 1 alternated the buffers nchunks times.
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            if (ch < nchunks) {
+              tmem_wait_ld();
+              // buffer parity must be a compile-time index: handle the two cases of nchunks parity explicitly
+              uint32_t pk[16];
+              const bool full = ch * 32 + 32 <= nvalid;
+              auto body = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+                if (ch + 1 < nchunks) tmem_ld32(tS + (ch + 1) * 32, nxt);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float p0 = fast_exp2(fmaf(__uint_as_float(cur[2 * i]), c, -mc));
+                  float p1 = fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), c, -mc));
+                  if (!full) {
+                    p0 = (ch * 32 + 2 * i < nvalid) ? p0 : 0.0f;
+                    p1 = (ch * 32 + 2 * i + 1 < nvalid) ? p1 : 0.0f;
+                  }
+                  lsum += p0 + p1;
+                  pk[i] = pack_bf16x2(p0, p1);
+                }
+              };
+              if ((nchunks + ch) & 1) body(v[1], v[0]); else body(v[0], v[1]);
+              tmem_st16(tS + ch * 16, pk);
+            }
+          }
+          tmem_wait_st();
+          l = l * alpha + lsum;
+          m = m_new;
+        }
+#else
         if (warp_live) {
           // pass 1: row maximum over the valid columns
           float mx = -INFINITY;
@@ -274,14 +374,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           l = l * alpha + lsum;
           m = m_new;
         }
+#endif
+        // O_FULL of the previous block must be observed BEFORE this block's P is published: once P_FULL(j) is
+        // complete the tensor core may finish P.V(j) and flip O_FULL again, and a parity wait that is lapped by two
+        // phase completions never returns. (The data of block j-1 is still safe afterwards: O is double-buffered.)
+        if (j > 0) {
+          mbar_wait(bar(O_FULL + t), (g - 1) & 1u);
+          tc_fence_after();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
+        if (lane == 0 && qd == 2) ATT_EV(210 + t);
         // fold in the previous block's P.V while the tensor core works on this one
         if (j > 0) accumulate_o(g - 1);
         alpha_prev = alpha;
       }
+      mbar_wait(bar(O_FULL + t), (g - 1) & 1u);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
+      tc_fence_after();
       accumulate_o(g - 1);
+      if (lane == 0 && qd == 2) ATT_EV(220 + t);
       tc_fence_before();
       // normalise and write the 64 output columns of this head
       if (qrow < p.Lq) {
@@ -297,6 +409,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           *(reinterpret_cast<uint4*>(orow) + i) = w;
         }
       }
+      if (lane == 0 && qd == 2) ATT_EV(230 + t);
     }
   }
 

@@ -406,6 +406,34 @@ static const AttnCase kAttnCases[] = {
     {"perf_siglip", 32, 16, 576, 576, true, false, 1.0f, 1, 10},
 };
 
+#ifdef ATT_TRACE
+extern "C" void b200enc_debug_attention_trace(long long* buf);
+static void run_attn_trace(int B, int H, int L) {
+  const int D = H * 64;
+  auto hq = rand_bf16(size_t(B) * L * 3 * D, 1.0f, false);
+  DevBuf dq(hq.size() * 2), dout(size_t(B) * L * D * 2), dtr(8 * 8000);
+  CK(cudaMemcpy(dq.p, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice));
+  uint16_t* base = (uint16_t*)dq.p;
+  auto call = [&]() {
+    return b200enc_attention(dq.p, (long long)L * 3 * D, 3 * D, base + D, base + 2 * D, (long long)L * 3 * D, 3 * D,
+                             dout.p, (long long)L * D, D, B, H, L, L, 64, 0.125f, 0, nullptr);
+  };
+  for (int i = 0; i < 3; ++i) call();
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(dtr.p, 0, dtr.bytes));
+  b200enc_debug_attention_trace((long long*)dtr.p);
+  call();
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(8000);
+  CK(cudaMemcpy(h.data(), dtr.p, h.size() * 8, cudaMemcpyDeviceToHost));
+  long long t0 = 1LL << 62;
+  for (int i = 0; i < 4000; ++i)
+    if (h[2 * i + 1] > 0) t0 = std::min(t0, h[2 * i + 1]);
+  for (int i = 0; i < 4000; ++i)
+    if (h[2 * i + 1] > 0) printf("EV %lld %lld\n", h[2 * i], h[2 * i + 1] - t0);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------ layernorm / stats
 static bool run_layernorm(int rows, int d, float eps, int row_mult, int iters) {
   printf("layernorm rows=%d d=%d eps=%g row_mult=%d\n", rows, d, eps, row_mult);
@@ -544,6 +572,12 @@ int main(int argc, char** argv) {
       ok = run_attn(c) && ok;
     }
   }
+#ifdef ATT_TRACE
+  if (which == "attn:trace") {
+    found = true;
+    run_attn_trace(argc > 2 ? atoi(argv[2]) : 128, argc > 3 ? atoi(argv[3]) : 12, argc > 4 ? atoi(argv[4]) : 197);
+  }
+#endif
   if (which == "rows:all") {
     found = true;
     ok = run_layernorm(1000, 768, 1e-6f, 1, 0) && ok;
