@@ -111,38 +111,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0, stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int qp = item % p.n_qp;
-        const int bh = item / p.n_qp;
-        const int h = bh % p.H;
-        const int b = bh / p.H;
-        const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
-        const uint32_t qb = it & 1u;
-        mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u);
+    // ------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
+    uint32_t it = 0, stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int qp = item % p.n_qp;
+      const int bh = item / p.n_qp;
+      const int h = bh % p.H;
+      const int b = bh / p.H;
+      const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
+      const uint32_t qb = it & 1u;
+      mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar(Q_FULL + qb), (two ? 2 : 1) * ATT_TILE_BYTES);
         const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
         tma_load_3d(&tmQ, bar(Q_FULL + qb), sq, h * ATT_HD, qp * 256, b);
         if (two) tma_load_3d(&tmQ, bar(Q_FULL + qb), sq + ATT_TILE_BYTES, h * ATT_HD, qp * 256 + ATT_BQ, b);
-        ATT_EV(10);
-        for (int j = 0; j < n_kvb; ++j) {
-          mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kvb; ++j) {
+        mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
           tma_load_3d(&tmV, bar(KV_FULL + stage), sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
-          ATT_EV(11);
-          if (++stage == ATT_KV_STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == ATT_KV_STAGES) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    {
       // The (item, kv-block) sequence of this CTA is walked as ONE stream: while block `cur` is being finished
       // (PV0, PV1) the score MMAs of the following block `nxt` — possibly the first block of the next item — are
       // already issued, so a tile's softmax never waits for the other tile's tail.
@@ -160,26 +162,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
         const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + bl.stage * ATT_TILE_BYTES, 16, 1024);
         const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma_of(bl.j), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k)
-          umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(bar(S_FULL + t));
-        ATT_EV(100 + t);
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(bar(S_FULL + t));
+        }
+        __syncwarp();
+        if (lane == 0) ATT_EV(100 + t);
       };
       auto issue_pv = [&](const Blk& bl, int t) {
         mbar_wait(bar(P_FULL + t), g[t] & 1u);
-        ATT_EV(110 + t);
+        if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
         const uint32_t sv = sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES;
         const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
         const int ksteps = n_mma_of(bl.j) / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
-          const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
-          umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) {
+            // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
+            const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
+            umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
+          }
+          umma_commit(bar(O_FULL + t));
         }
-        umma_commit(bar(O_FULL + t));
-        ATT_EV(120 + t);
+        __syncwarp();
+        if (lane == 0) ATT_EV(120 + t);
         ++g[t];
       };
       // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
@@ -187,13 +195,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (t_first == 0) {
           if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u);
           mbar_wait(bar(KV_FULL + bl.stage), bl.phase);
-          ATT_EV(130);
+          if (lane == 0) ATT_EV(130);
           tc_fence_after();
         }
         for (int t = t_first; t <= t_last; ++t)
           if (t == 0 || bl.two) issue_qk(bl, t);
         // after the last score MMA that reads this item's Q tiles has been issued, hand the Q buffer back
-        if (t_last == 1 && bl.j == n_kvb - 1) umma_commit(bar(Q_EMPTY + (bl.it & 1u)));
+        if (t_last == 1 && bl.j == n_kvb - 1) {
+          if (elect_one()) umma_commit(bar(Q_EMPTY + (bl.it & 1u)));
+          __syncwarp();
+        }
       };
       auto advance = [&](Blk bl) {
         if (++bl.stage == ATT_KV_STAGES) {
@@ -220,7 +231,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (more) start_block(nxt, 0, 0);
           if (cur.two) issue_pv(cur, 1);
           if (more) start_block(nxt, 1, 1);
-          umma_commit(bar(KV_EMPTY + cur.stage));  // K/V of `cur` are free once everything issued so far completes
+          if (elect_one()) umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
+          __syncwarp();
           if (!more) break;
           cur = nxt;
         }

@@ -153,17 +153,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tile_step = gridDim.x / kCtas;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one per CTA)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int b = tile / tiles_per_batch;
-        const int r = tile - b * tiles_per_batch;
-        const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;
-        const int n0 = (r % p.tiles_n) * GEMM_BN + int(cta_rank) * kBRows;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = ring + stage * kStageBytes;
+    // ------------------------------------------------------------ TMA producer (one warp per CTA, converged;
+    // a single elected lane issues, so tensor-map / barrier operands stay in uniform registers)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;
+      const int n0 = (r % p.tiles_n) * GEMM_BN + int(cta_rank) * kBRows;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = ring + stage * kStageBytes;
+        if (elect_one()) {
           if (kCtas == 2) {
             // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
             const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
@@ -175,16 +176,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_3d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0, b);
             tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only; converged warp)
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -197,21 +199,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = ring + stage * kStageBytes;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if (kCtas == 2)
-              umma_ss_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advancing K by 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              if (kCtas == 2)
+                umma_ss_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (kCtas == 2) umma_commit_2cta(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) {
+              if (kCtas == 2) umma_commit_2cta(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+            }
           }
-          if (kCtas == 2) umma_commit_2cta(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (kCtas == 2) umma_commit_2cta(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -367,7 +374,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kTmaStore) {
           // with two buffers the store that last used this one was issued a whole tile ago: no drain on the critical path
           constexpr int kBufOff = SM::kStgBufs == 2 ? GEMM_STG_BYTES : 0;
-          if (lane == 0) tma_store_wait_read<SM::kStgBufs - 1>();
+          if (elect_one()) tma_store_wait_read<SM::kStgBufs - 1>();
           __syncwarp();
           uint8_t* dst = stg_ptr + cc * kBufOff + lane * 128;
 #pragma unroll
@@ -377,7 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {  // bulk groups are per thread: elect.sync picks the same lane of a full warp every time
             tma_store_3d(&tmC, stg + cc * kBufOff, nc, m0 + q * 32, b);
             tma_store_commit();
           }
@@ -410,7 +417,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (kTmaStore && lane == 0) tma_store_wait_all<0>();
+    if (kTmaStore && elect_one()) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

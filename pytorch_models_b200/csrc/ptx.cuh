@@ -15,6 +15,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a fully converged warp. Single-thread instructions (tcgen05.mma / commit, TMA) are issued as
+// `if (elect_one()) {...}` from warp-uniform control flow: their descriptor operands then stay in uniform registers,
+// whereas code under `if (lane == 0)` makes the compiler wrap every such instruction in a vote/elect loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
