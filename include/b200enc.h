@@ -81,7 +81,8 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
  * transformer.py:52 together with the head split/merge views at :47-49 and :53: q, k, v are column slices of the
  * projection output (row strides ldq / ldkv, head h at columns [64h, 64h+64)), the result is head-interleaved
  * [B, Lq, H*64] ready for out_proj. head_dim must be 64 (every BASELINE config). Lq != Lkv is allowed
- * (the 1-query MAP pooling head, image/vit.py:41). flags is reserved (pass 0).
+ * (the 1-query MAP pooling head, image/vit.py:41). K/V stream in blocks of 128 rows with an online
+ * softmax; flags is reserved (pass 0).
  */
 int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                       long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,

@@ -51,12 +51,12 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_batch_stride = out_batch_stride;
   p.ldo = ldo;
+  (void)flags;
 #ifdef ATT_TRACE
   p.trace = g_attention_trace;
 #else
   p.trace = nullptr;
 #endif
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  (void)flags;
   return launch_attention(tq, tk, tv, p, s);
 }

@@ -175,15 +175,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(bar(P_FULL + t), g[t] & 1u);
         if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
-        const uint32_t sv = sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES;
+        // descriptors are built outside the elected branch (uniform registers); per K step only immediates change:
+        // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes (+128 in the descriptor); P: 8 TMEM columns
+        const uint64_t dv0 = make_smem_desc_sw128(sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES, 16, 1024);
+        const uint32_t pa0 = tmem_base + t * 256;
         const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
         const int ksteps = n_mma_of(bl.j) / 16;
         if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) {
-            // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes per K step; P: 8 TMEM columns per step
-            const uint64_t dv = make_smem_desc_sw128(sv + k * 2048, 16, 1024);
-            umma_ts(d_o, tmem_base + t * 256 + 8u * k, dv, idesc_o, k != 0 ? 1u : 0u);
-          }
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k)
+            if (k < ksteps) umma_ts(d_o, pa0 + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : 0u);
           umma_commit(bar(O_FULL + t));
         }
         __syncwarp();

@@ -367,7 +367,7 @@ static bool run_attn(const AttnCase& c) {
     }
   }
   bool ok = report(c.name, st);
-  if (ok && c.time_iters > 0) {
+  if ((ok || getenv("B200_DEBUG_FLAGS")) && c.time_iters > 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -399,6 +399,12 @@ static const AttnCase kAttnCases[] = {
     {"l576_tmem", 1, 2, 576, 576, true, false, 2.0f, 0, 0},
     {"l1370_tmem", 1, 2, 1370, 1370, true, false, 3.0f, 1, 0},
     {"cross_q1", 3, 2, 1, 576, false, false, 2.0f, 0, 0},
+    {"l16", 3, 2, 16, 16, true, false, 2.0f, 0, 0},
+    {"l130", 2, 2, 130, 130, true, false, 2.0f, 0, 0},
+    {"l256", 2, 2, 256, 256, true, false, 2.0f, 0, 0},
+    {"cross_q300_kv200", 2, 2, 300, 200, false, false, 2.0f, 0, 0},
+    {"cross_q1_kv200", 5, 3, 1, 200, false, false, 2.0f, 0, 0},
+    {"many_short", 150, 4, 197, 197, true, false, 2.0f, 10, 0},
     {"many_items", 40, 12, 197, 197, true, false, 2.0f, 6, 0},
     {"perf_vitb", 128, 12, 197, 197, true, false, 1.0f, 2, 20},
     {"perf_vitb_smem", 128, 12, 197, 197, true, true, 1.0f, 2, 20},
