@@ -241,6 +241,12 @@ def main() -> None:
         for _ in range(warmup):
             y = model(x_dev)
         barrier()
+        if os.environ.get("B200_PROFILE_STEP"):
+            # ncu --profile-from-start off: capture exactly one warmed-up forward (scripts/gpu_ncu.sh)
+            torch.cuda.profiler.start()
+            y = model(x_dev)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         sampler = ClockSampler(local) if rank == 0 else None
         launches0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -433,10 +433,16 @@ static void run_attn_trace(int B, int H, int L) {
   std::vector<long long> h(8000);
   CK(cudaMemcpy(h.data(), dtr.p, h.size() * 8, cudaMemcpyDeviceToHost));
   long long t0 = 1LL << 62;
-  for (int i = 0; i < 4000; ++i)
+  for (int i = 0; i < 3950; ++i)
     if (h[2 * i + 1] > 0) t0 = std::min(t0, h[2 * i + 1]);
-  for (int i = 0; i < 4000; ++i)
+  for (int i = 0; i < 3950; ++i)
     if (h[2 * i + 1] > 0) printf("EV %lld %lld\n", h[2 * i], h[2 * i + 1] - t0);
+  for (int w = 0; w < 2; ++w) {
+    const long long* a = &h[7900 + 8 * w];
+    if (a[5] > 0)
+      printf("ACC wg%d blocks=%lld per block: pass1 ld+wait %lld, pass1 total %lld, pass2 ld+wait %lld, pass2 total %lld, "
+             "between passes %lld\n", w, a[5], a[0] / a[5], a[1] / a[5], a[2] / a[5], a[3] / a[5], (a[4] - a[1]) / a[5]);
+  }
 }
 #endif
 
