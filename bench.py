@@ -340,7 +340,12 @@ def main() -> None:
             "kernel": "gemm_bf16_kernel (b200enc_linear: QKV / out_proj / FC1 / FC2 / patch embed)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["sustained"], "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['burst']})",
-            "frac_of_burst": achieved / peaks["burst"], "traffic": None,
+            "frac_of_burst": achieved / peaks["burst"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` capture of one
+            # encoder layer at this config (profiles/r01/ncu_full_layer_summary.md), mean over the four GEMM shapes;
+            # algorithmic bytes for the same four launches average 1.39e9
+            "traffic": 1.39e9 if (args.config == "c2" and B == 1024) else None,
+            "traffic_source": "ncu --set full, profiles/r01/ncu_full_layer_summary.md (QKV 1.20, out_proj 0.91, FC1 1.51, FC2 1.93 GB)",
             "launches_per_step": by_kernel["b200enc_linear"][1], "avg_launch_ms": gemm_ms / by_kernel["b200enc_linear"][1],
             "share_of_step": gemm_ms / total_ms,
             "by_shape": {k: {"launches": v[2], "avg_ms": round(v[0] / v[2], 4), "tflops": round(v[1] / v[0] * 1e-9, 1)}

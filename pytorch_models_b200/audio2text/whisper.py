@@ -90,3 +90,28 @@ class WhisperEncoder(nn.Module):
         out = torch.empty_like(h)
         ops.layernorm(h.view(N * L, d), gamma, beta, self.norm.eps, out.view(N * L, d))
         return out if out_dtype == torch.bfloat16 else out.to(out_dtype)
+
+    @torch.no_grad()
+    def load_openai_state_dict(self, state_dict: dict) -> None:
+        """Encoder half of an openai-whisper checkpoint (``model_state_dict``), cf. whisper.py:97-135."""
+        sd = {k[len("encoder."):]: v for k, v in state_dict.items() if k.startswith("encoder.")}
+
+        def take(module, key: str) -> None:
+            module.weight.copy_(sd.pop(f"{key}.weight"))
+            if module.bias is not None:
+                module.bias.copy_(sd.pop(f"{key}.bias", 0))  # the key projection has no bias in the checkpoint
+
+        take(self.stem[0], "conv1")
+        take(self.stem[2], "conv2")
+        self.pos_embs.copy_(sd.pop("positional_embedding"))
+        for i, layer in enumerate(self.layers):
+            pre = f"blocks.{i}"
+            take(layer.sa.q_proj, f"{pre}.attn.query")
+            take(layer.sa.k_proj, f"{pre}.attn.key")
+            take(layer.sa.v_proj, f"{pre}.attn.value")
+            take(layer.sa.out_proj, f"{pre}.attn.out")
+            take(layer.sa_norm, f"{pre}.attn_ln")
+            take(layer.mlp.linear1, f"{pre}.mlp.0")
+            take(layer.mlp.linear2, f"{pre}.mlp.2")
+            take(layer.mlp_norm, f"{pre}.mlp_ln")
+        take(self.norm, "ln_post")

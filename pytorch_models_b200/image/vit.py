@@ -170,6 +170,17 @@ class ViT(nn.Module):
         grid = F.interpolate(grid, (new, new), mode=interpolation_mode)
         self.pe = nn.Parameter(grid.permute(0, 2, 3, 1).flatten(1, 2))
 
+    # -- weight loading (host side; mirrors load_flax_ckpt / load_facebook_state_dict, vit.py:151-200,257-306) ------
+    def load_flax_arrays(self, arrays: dict, *, big_vision: bool = False) -> None:
+        from .vit_weights import load_flax_arrays
+
+        load_flax_arrays(self, arrays, big_vision=big_vision)
+
+    def load_facebook_state_dict(self, state_dict: dict) -> None:
+        from .vit_weights import load_facebook_state_dict
+
+        load_facebook_state_dict(self, state_dict)
+
     # -- constructors --------------------------------------------------------------------------
     @staticmethod
     def _parse(model_tag: str, default_weights: str) -> tuple[str, int, str]:

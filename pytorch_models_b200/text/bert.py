@@ -45,3 +45,55 @@ class BERT(nn.Module):
         ops.layernorm(emb3.view(B * L, d), gamma, beta, self.norm.eps, h.view(B * L, d))
         y = self.layers.run(h).reshape(*x.shape, d)
         return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+
+    @staticmethod
+    def from_hf(model_tag: str, *, pretrained: bool = False, **kwargs) -> "BERT":
+        """Build from a HuggingFace config (bert.py:41-73); needs network access for the config / checkpoint."""
+        import json
+
+        import requests
+
+        config = None
+        for tag in (model_tag, f"gaunernst/{model_tag}"):
+            resp = requests.get(f"https://huggingface.co/{tag}/raw/main/config.json")
+            if resp.ok:
+                config, model_tag = json.loads(resp.content), tag
+                break
+        if config is None:
+            raise ValueError(f"Unsupported model {model_tag}")
+        max_len = config["max_position_embeddings"] - (2 if "roberta" in config["model_type"] else 0)
+        m = BERT(config["vocab_size"], config["num_hidden_layers"], config["hidden_size"], max_len,
+                 norm_eps=config["layer_norm_eps"], **kwargs)
+        if pretrained:
+            url = f"https://huggingface.co/{model_tag}/resolve/main/pytorch_model.bin"
+            m.load_hf_state_dict(torch.hub.load_state_dict_from_url(url, file_name=model_tag.replace("/", "_")))
+        return m
+
+    @torch.no_grad()
+    def load_hf_state_dict(self, state_dict: dict) -> None:
+        """HF BERT / RoBERTa checkpoint -> this layout (bert.py:75-107): token-type embedding 0 is merged into the
+        position table, RoBERTa's two unused leading positions are dropped."""
+        roberta = any(k.startswith("roberta.") for k in state_dict)
+        sd = {k.removeprefix("bert.").removeprefix("roberta."): v for k, v in state_dict.items()}
+
+        def take(module, key: str) -> None:
+            module.weight.copy_(sd.pop(f"{key}.weight"))
+            if module.bias is not None:
+                module.bias.copy_(sd.pop(f"{key}.bias"))
+
+        words = sd.pop("embeddings.word_embeddings.weight")
+        self.token_embs.weight[: words.shape[0]] = words
+        pos = sd.pop("embeddings.position_embeddings.weight")
+        pos = pos[2:] if roberta else pos
+        self.pos_embs.copy_(pos + sd.pop("embeddings.token_type_embeddings.weight")[0])
+        take(self.norm, "embeddings.LayerNorm")
+        for i, layer in enumerate(self.layers):
+            pre = f"encoder.layer.{i}"
+            take(layer.sa.q_proj, f"{pre}.attention.self.query")
+            take(layer.sa.k_proj, f"{pre}.attention.self.key")
+            take(layer.sa.v_proj, f"{pre}.attention.self.value")
+            take(layer.sa.out_proj, f"{pre}.attention.output.dense")
+            take(layer.sa_norm, f"{pre}.attention.output.LayerNorm")
+            take(layer.mlp.linear1, f"{pre}.intermediate.dense")
+            take(layer.mlp.linear2, f"{pre}.output.dense")
+            take(layer.mlp_norm, f"{pre}.output.LayerNorm")

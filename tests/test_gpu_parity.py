@@ -161,3 +161,21 @@ def test_encoder_accepts_leading_dims_and_strided_input():
     assert got.shape == x.shape and got.dtype == torch.float32
     max_abs, min_cos = error_stats(got.cpu().numpy().reshape(6, -1), want.numpy().reshape(6, -1))
     assert max_abs <= 0.06 and min_cos >= MIN_COS, (max_abs, min_cos)
+
+
+def test_cuda_graph_replay_is_bit_identical(golden):
+    """The whole forward is capturable (no host sync / allocation inside the library) and replays bit-exactly."""
+    from pytorch_models_b200.graphs import GraphedForward
+
+    g = golden("vit_cls")
+    m = build_model(g).cuda().bfloat16()
+    x = torch.from_numpy(np.array(g.input)).cuda().bfloat16()
+    with torch.no_grad():
+        eager = m(x)
+        graphed = GraphedForward(m, x)
+        y1 = graphed(x)
+        x2 = torch.randn_like(x)
+        y2 = graphed(x2)
+        assert torch.equal(y1, eager) and torch.equal(y2, m(x2))
+    with pytest.raises(ValueError):
+        graphed(x[:1])
