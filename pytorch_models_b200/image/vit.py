@@ -148,6 +148,8 @@ class ViT(nn.Module):
 
     def forward(self, imgs: Tensor) -> Tensor:
         out_dtype = imgs.dtype if imgs.dtype in (torch.bfloat16, torch.float32) else torch.float32
+        if imgs.shape[0] == 0:
+            return torch.empty(0, self.norm.normalized_shape[0], device=imgs.device, dtype=out_dtype)
         x = self.layers.run(self.embed(imgs))
         N, L, d = x.shape
         gamma, beta = norm_vectors(self.norm)

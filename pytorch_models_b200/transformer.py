@@ -394,7 +394,7 @@ class Encoder(nn.Sequential):
     def run(self, x3: Tensor) -> Tensor:
         """bf16 contiguous (B, L, d) -> new tensor of the same shape; x3 is left untouched."""
         layers = list(self)
-        if not layers:
+        if not layers or x3.numel() == 0:
             return x3.clone()
         B, L, _ = x3.shape
         ws = layers[0].workspace(B, L, x3.device)
