@@ -51,6 +51,26 @@ struct DevBuf {
   ~DevBuf() { cudaFree(p); }
 };
 
+// Device buffer with 4 KB guard bands on both sides (compute-sanitizer is closed on this pool: out-of-bounds writes
+// of the st.global paths are caught by checking that the bands still hold their fill pattern).
+struct GuardedBuf {
+  static constexpr size_t kGuard = 4096;
+  DevBuf raw;
+  size_t bytes;
+  explicit GuardedBuf(size_t b) : raw(b + 2 * kGuard), bytes(b) { CK(cudaMemset(raw.p, 0x5a, raw.bytes)); }
+  void* p() const { return static_cast<char*>(raw.p) + kGuard; }
+  bool intact(const char* what) const {
+    std::vector<unsigned char> h(raw.bytes);
+    CK(cudaMemcpy(h.data(), raw.p, raw.bytes, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < kGuard; ++i)
+      if (h[i] != 0x5a || h[kGuard + bytes + i] != 0x5a) {
+        printf("  [FAIL] %s: guard band overwritten at %s%zu\n", what, h[i] != 0x5a ? "-" : "+", i);
+        return false;
+      }
+    return true;
+  }
+};
+
 static std::vector<uint16_t> rand_bf16(size_t n, float scale, bool ints) {
   std::vector<uint16_t> v(n);
   for (size_t i = 0; i < n; ++i) v[i] = f2bf(ints ? float(int(rnd() % 5) - 2) : urand() * scale);
@@ -149,7 +169,8 @@ static bool run_linear(const LinearCase& c) {
   const int flags = (c.gelu ? B200ENC_LINEAR_GELU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
   const int n_slices = (N + 127) / 128;
   const bool want_stats = c.res && !c.fold && !c.direct;
-  DevBuf dso(size_t(B) * M * n_slices * 8);
+  GuardedBuf gso(size_t(B) * M * n_slices * 8);
+  struct { void* p; } dso = {gso.p()};
   auto call = [&]() {
     b200enc_linear_args a;
     memset(&a, 0, sizeof(a));
@@ -233,6 +254,7 @@ static bool run_linear(const LinearCase& c) {
         }
     ok = report("fused_stats", ss) && ok;
   }
+  ok = gso.intact("stats_out") && ok;
 
   if ((ok || dbg) && c.time_iters > 0) {
     cudaEvent_t e0, e1;
@@ -312,7 +334,9 @@ static bool run_attn(const AttnCase& c) {
     koff = 0;
     voff = D;
   }
-  DevBuf dq(hq.size() * 2), dkv(hkv.size() * 2 + 16), dout(size_t(B) * Lq * D * 2);
+  DevBuf dq(hq.size() * 2), dkv(hkv.size() * 2 + 16);
+  GuardedBuf gout(size_t(B) * Lq * D * 2);
+  struct { void* p; size_t bytes; } dout = {gout.p(), gout.bytes};
   CK(cudaMemcpy(dq.p, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice));
   if (!c.self_qkv) CK(cudaMemcpy(dkv.p, hkv.data(), hkv.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));
@@ -367,6 +391,7 @@ static bool run_attn(const AttnCase& c) {
     }
   }
   bool ok = report(c.name, st);
+  ok = gout.intact(c.name) && ok;
   if ((ok || getenv("B200_DEBUG_FLAGS")) && c.time_iters > 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -453,7 +478,9 @@ static bool run_layernorm(int rows, int d, float eps, int row_mult, int iters) {
   auto hx = rand_bf16(size_t(rows) * ldx, 2.0f, false);
   for (size_t i = 0; i < hx.size(); ++i) hx[i] = f2bf(bf2f(hx[i]) + 0.7f);  // non-zero mean
   auto hg = rand_f32(d, 1.0f), hb = rand_f32(d, 0.5f);
-  DevBuf dx(hx.size() * 2), dg(d * 4), db(d * 4), dout(size_t(rows) * d * 2), dst(size_t(rows) * 8), dst2(size_t(rows) * 8);
+  DevBuf dx(hx.size() * 2), dg(d * 4), db(d * 4), dst2(size_t(rows) * 8);
+  GuardedBuf gout(size_t(rows) * d * 2), gst(size_t(rows) * 8);
+  struct { void* p; } dout = {gout.p()}, dst = {gst.p()};
   CK(cudaMemcpy(dx.p, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dg.p, hg.data(), d * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db.p, hb.data(), d * 4, cudaMemcpyHostToDevice));
@@ -492,6 +519,7 @@ static bool run_layernorm(int rows, int d, float eps, int row_mult, int iters) {
   }
   bool ok = report("layernorm", st);
   ok = report("row_stats", ss) && ok;
+  ok = gout.intact("layernorm out") && gst.intact("layernorm stats") && ok;
   if (ok && iters > 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
