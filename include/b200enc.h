@@ -24,6 +24,7 @@ const char* b200enc_last_error(void);
 
 /* flags for b200enc_linear */
 #define B200ENC_LINEAR_GELU 1          /* exact (erf) GELU after bias: nn.GELU(), transformer.py:61 */
+#define B200ENC_LINEAR_GELU_TANH 2     /* tanh GELU after bias: nn.GELU(approximate="tanh"), transformer.py:62 (no residual) */
 #define B200ENC_LINEAR_DIRECT_STORE 256 /* debug: per-thread st.global epilogue without the smem transpose */
 #define B200ENC_LINEAR_ONE_CTA 512      /* debug: 128-row tiles on single CTAs instead of 256-row tiles on CTA pairs */
 
@@ -37,7 +38,7 @@ const char* b200enc_last_error(void);
  *   epi(acc) = acc + bias[n]                                        (colsum == NULL)
  *            = rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]           (LayerNorm folded into the GEMM: w must be
  *              gamma-scaled, colsum[n] = sum_k w[n][k], bias[n] = W.beta + b)
- *   then GELU if flags & B200ENC_LINEAR_GELU, then + residual[b][m][n] if residual != NULL
+ *   then GELU if flags & B200ENC_LINEAR_GELU (or its tanh form with B200ENC_LINEAR_GELU_TANH), then + residual[b][m][n] if residual != NULL
  *   (res_batch_stride == 0 broadcasts one [M, N] table over the batch: the positional embedding).
  *
  * Row statistics of the folded LayerNorm come in one of two forms:
@@ -74,6 +75,9 @@ typedef struct b200enc_linear_args {
 
 int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
+/* flags for b200enc_attention */
+#define B200ENC_ATTN_CAUSAL 1 /* key j only visible to queries i >= j (is_causal=True of SDPA: DecoderLayer, transformer.py:97) */
+
 /*
  * out[b][i][64h + :] = softmax_j( q[b][i][64h + :] . k[b][j][64h + :] * scale ) v[b][j][64h + :]
  *
@@ -82,7 +86,7 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
  * projection output (row strides ldq / ldkv, head h at columns [64h, 64h+64)), the result is head-interleaved
  * [B, Lq, H*64] ready for out_proj. head_dim must be 64 (every BASELINE config). Lq != Lkv is allowed
  * (the 1-query MAP pooling head, image/vit.py:41). K/V stream in blocks of 128 rows with an online
- * softmax; flags is reserved (pass 0).
+ * softmax. With B200ENC_ATTN_CAUSAL the K/V blocks above the diagonal are skipped entirely.
  */
 int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                       long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
@@ -116,6 +120,15 @@ int b200enc_patch_rows(const void* img, int img_dtype, int B, int H, int W, int 
 
 /* tokens[b][0][:] = cls[:] for every image (torch.cat([cls_token, out], -2) at image/vit.py:80-81). */
 int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, long long batch_stride, void* stream);
+
+/*
+ * Token + position embedding: out[r][:] = bf16(tok[ids[r]][:] + pos[r % L][:]) for r < rows (= batch * L).
+ * Replaces `self.token_embs(x) + self.pos_embs[:L]` (text/bert.py:35-36, text/gpt2.py:22-23, text/gpt.py:25-26,
+ * audio2text/whisper.py:47-48). ids: int64 device pointer; tok [vocab, d] and pos [>= L, d] contiguous, both `dtype`
+ * (B200ENC_DTYPE_*); d % 8 == 0; out [rows, d] bf16 contiguous. A row whose id is outside [0, vocab) is set to NaN.
+ */
+int b200enc_embed_rows(const long long* ids, long long rows, int L, const void* tok, const void* pos, int dtype,
+                       int vocab, int d, void* out, void* stream);
 
 /*
  * rows[n][t + 1][c] = x[n][c][t], rows[n][0] = rows[n][T + 1] = 0   (x: (N, C, T) fp32/bf16 -> (N, T+2, C) bf16).

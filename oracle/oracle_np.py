@@ -43,18 +43,28 @@ def gelu(x: np.ndarray) -> np.ndarray:
     return (0.5 * x * (1.0 + erf(x / np.sqrt(2.0)))).astype(F32)
 
 
-def sdpa(q: np.ndarray, k: np.ndarray, v: np.ndarray) -> np.ndarray:
-    """F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0, is_causal=False) (transformer.py:52):
-    softmax(q k^T / sqrt(head_dim)) v over (..., heads, L, head_dim)."""
+def gelu_tanh(x: np.ndarray) -> np.ndarray:
+    """nn.GELU(approximate="tanh") (transformer.py:62)."""
+    return (0.5 * x * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * x ** 3)))).astype(F32)
+
+
+def sdpa(q: np.ndarray, k: np.ndarray, v: np.ndarray, causal: bool = False) -> np.ndarray:
+    """F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0, is_causal=causal) (transformer.py:52):
+    softmax(q k^T / sqrt(head_dim)) v over (..., heads, L, head_dim); with is_causal, query i sees keys j <= i
+    (lower-triangular mask aligned at the top-left corner)."""
     s = (q @ np.swapaxes(k, -1, -2)) * F32(1.0 / np.sqrt(q.shape[-1]))
+    if causal:
+        Lq, Lk = s.shape[-2:]
+        s = np.where(np.tril(np.ones((Lq, Lk), dtype=bool)), s, F32(-np.inf))
     s = s - s.max(-1, keepdims=True)
     p = np.exp(s)
     p = p / p.sum(-1, keepdims=True, dtype=F32)
     return (p @ v).astype(F32)
 
 
-def mha(sd: dict, prefix: str, q_in: np.ndarray, kv_in: np.ndarray | None, n_heads: int) -> np.ndarray:
-    """MHA.forward (transformer.py:36-53) with k = v = kv_in (or q_in when kv_in is None), no bias, not causal."""
+def mha(sd: dict, prefix: str, q_in: np.ndarray, kv_in: np.ndarray | None, n_heads: int,
+        causal: bool = False) -> np.ndarray:
+    """MHA.forward (transformer.py:36-53) with k = v = kv_in (or q_in when kv_in is None), attn_bias None."""
     kv_in = q_in if kv_in is None else kv_in
 
     def heads(t: np.ndarray) -> np.ndarray:  # (*, L, h*hd) -> (*, h, L, hd)   transformer.py:47-49
@@ -63,15 +73,16 @@ def mha(sd: dict, prefix: str, q_in: np.ndarray, kv_in: np.ndarray | None, n_hea
     q = heads(linear(q_in, sd[prefix + "q_proj.weight"], sd.get(prefix + "q_proj.bias")))
     k = heads(linear(kv_in, sd[prefix + "k_proj.weight"], sd.get(prefix + "k_proj.bias")))
     v = heads(linear(kv_in, sd[prefix + "v_proj.weight"], sd.get(prefix + "v_proj.bias")))
-    o = sdpa(q, k, v)
+    o = sdpa(q, k, v, causal)
     o = np.swapaxes(o, -2, -3)
     o = o.reshape(*o.shape[:-2], -1)  # transformer.py:53
     return linear(o, sd[prefix + "out_proj.weight"], sd.get(prefix + "out_proj.bias"))
 
 
-def mlp(sd: dict, prefix: str, x: np.ndarray) -> np.ndarray:
+def mlp(sd: dict, prefix: str, x: np.ndarray, act: str = "gelu") -> np.ndarray:
     """MLP: linear1 -> GELU -> linear2 -> dropout(eval = identity) (transformer.py:56-67)."""
-    h = gelu(linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
+    fn = gelu_tanh if act == "approximate_gelu" else gelu
+    h = fn(linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
     return linear(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
 
 
@@ -87,6 +98,34 @@ def encoder_layer(sd: dict, prefix: str, x: np.ndarray, n_heads: int, pre_norm: 
         x = ln("sa_norm", x + mha(sd, prefix + "sa.", x, None, n_heads))
         x = ln("mlp_norm", x + mlp(sd, prefix + "mlp.", x))
     return x.astype(F32)
+
+
+def decoder_layer(sd: dict, prefix: str, x: np.ndarray, memory: np.ndarray | None, n_heads: int, pre_norm: bool,
+                  eps: float, act: str = "gelu") -> np.ndarray:
+    """DecoderLayer.forward (transformer.py:95-105); cross-attention iff the state dict holds ``ca.*``."""
+    def ln(name: str, t: np.ndarray) -> np.ndarray:
+        return layer_norm(t, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"], eps)
+
+    cross = prefix + "ca.q_proj.weight" in sd
+    if pre_norm:  # transformer.py:97-99
+        x = x + mha(sd, prefix + "sa.", ln("sa_norm", x), None, n_heads, causal=True)
+        if cross:
+            x = x + mha(sd, prefix + "ca.", ln("ca_norm", x), memory, n_heads)
+        x = x + mlp(sd, prefix + "mlp.", ln("mlp_norm", x), act)
+    else:  # transformer.py:101-103
+        x = ln("sa_norm", x + mha(sd, prefix + "sa.", x, None, n_heads, causal=True))
+        if cross:
+            x = ln("ca_norm", x + mha(sd, prefix + "ca.", x, memory, n_heads))
+        x = ln("mlp_norm", x + mlp(sd, prefix + "mlp.", x, act))
+    return x.astype(F32)
+
+
+def decoder(sd: dict, x: np.ndarray, memory: np.ndarray | None, n_heads: int, pre_norm: bool, eps: float,
+            act: str = "gelu", prefix: str = "layers.") -> np.ndarray:
+    """Decoder.forward (transformer.py:173-176)."""
+    for i in range(n_layers_of(sd, prefix)):
+        x = decoder_layer(sd, f"{prefix}{i}.", x, memory, n_heads, pre_norm, eps, act)
+    return x
 
 
 def n_layers_of(sd: dict, prefix: str = "layers.") -> int:
@@ -159,3 +198,41 @@ def bert_forward(sd: dict, tokens: np.ndarray, eps: float = 1e-12) -> np.ndarray
     x = sd["token_embs.weight"][tokens] + sd["pos_embs"][: tokens.shape[-1]]
     x = layer_norm(x.astype(F32), sd["norm.weight"], sd["norm.bias"], eps)
     return encoder(sd, x, x.shape[-1] // 64, False, eps)
+
+
+def sub_dict(sd: dict, prefix: str) -> dict:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def lm_embed(sd: dict, tokens: np.ndarray) -> np.ndarray:
+    """token_embs(x) + pos_embs[:L] (gpt2.py:22-23, gpt.py:25-26, whisper.py:47-48)."""
+    return (sd["token_embs.weight"][tokens] + sd["pos_embs"][: tokens.shape[-1]]).astype(F32)
+
+
+def whisper_decoder_forward(sd: dict, tokens: np.ndarray, memory: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """WhisperDecoder.forward (whisper.py:46-52)."""
+    x = lm_embed(sd, tokens)
+    x = decoder(sd, x, memory, x.shape[-1] // 64, True, eps)
+    x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+    return (x @ sd["token_embs.weight"].T).astype(F32)
+
+
+def whisper_forward(sd: dict, x: np.ndarray, targets: np.ndarray) -> np.ndarray:
+    """Whisper.forward (whisper.py:62-63)."""
+    memory = whisper_encoder_forward(sub_dict(sd, "encoder."), x)
+    return whisper_decoder_forward(sub_dict(sd, "decoder."), targets, memory)
+
+
+def gpt2_forward(sd: dict, tokens: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """GPT2.forward (gpt2.py:21-27)."""
+    x = lm_embed(sd, tokens)
+    x = decoder(sd, x, None, x.shape[-1] // 64, True, eps, "approximate_gelu")
+    x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+    return (x @ sd["token_embs.weight"].T).astype(F32)
+
+
+def gpt_forward(sd: dict, tokens: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """GPT.forward (gpt.py:24-29)."""
+    x = lm_embed(sd, tokens)
+    x = decoder(sd, x, None, x.shape[-1] // 64, False, eps, "approximate_gelu")
+    return (x @ sd["token_embs.weight"].T).astype(F32)

@@ -20,21 +20,23 @@ def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def mha(sd: dict, prefix: str, q_in: Tensor, kv_in: Tensor | None, n_heads: int) -> Tensor:
-    """MHA.forward (transformer.py:36-53), k = v = kv_in (self-attention when None), no mask."""
+def mha(sd: dict, prefix: str, q_in: Tensor, kv_in: Tensor | None, n_heads: int, causal: bool = False) -> Tensor:
+    """MHA.forward (transformer.py:36-53), k = v = kv_in (self-attention when None), attn_bias None."""
     kv_in = q_in if kv_in is None else kv_in
 
     def proj(name: str, t: Tensor) -> Tensor:
         y = F.linear(t, sd[f"{prefix}{name}.weight"], sd.get(f"{prefix}{name}.bias"))
         return y.unflatten(-1, (n_heads, -1)).transpose(-2, -3)
 
-    o = F.scaled_dot_product_attention(proj("q_proj", q_in), proj("k_proj", kv_in), proj("v_proj", kv_in))
+    o = F.scaled_dot_product_attention(proj("q_proj", q_in), proj("k_proj", kv_in), proj("v_proj", kv_in),
+                                       is_causal=causal)
     return F.linear(o.transpose(-2, -3).flatten(-2), sd[prefix + "out_proj.weight"], sd.get(prefix + "out_proj.bias"))
 
 
-def mlp(sd: dict, prefix: str, x: Tensor) -> Tensor:
-    """MLP (transformer.py:56-67): linear1 -> exact GELU -> linear2."""
-    h = F.gelu(F.linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
+def mlp(sd: dict, prefix: str, x: Tensor, act: str = "gelu") -> Tensor:
+    """MLP (transformer.py:56-67): linear1 -> GELU (exact, or tanh form for act="approximate_gelu", :61-62) -> linear2."""
+    h = F.gelu(F.linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]),
+               approximate="tanh" if act == "approximate_gelu" else "none")
     return F.linear(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
 
 
@@ -48,6 +50,32 @@ def encoder_layer(sd: dict, prefix: str, x: Tensor, n_heads: int, pre_norm: bool
         return x + mlp(sd, prefix + "mlp.", ln("mlp_norm", x))
     x = ln("sa_norm", x + mha(sd, prefix + "sa.", x, None, n_heads))
     return ln("mlp_norm", x + mlp(sd, prefix + "mlp.", x))
+
+
+def decoder_layer(sd: dict, prefix: str, x: Tensor, memory: Tensor | None, n_heads: int, pre_norm: bool, eps: float,
+                  act: str = "gelu") -> Tensor:
+    """DecoderLayer.forward (transformer.py:95-105); cross-attention iff the state dict holds ``ca.*``."""
+    def ln(name: str, t: Tensor) -> Tensor:
+        return layer_norm(t, sd[f"{prefix}{name}.weight"], sd[f"{prefix}{name}.bias"], eps)
+
+    cross = f"{prefix}ca.q_proj.weight" in sd
+    if pre_norm:
+        x = x + mha(sd, prefix + "sa.", ln("sa_norm", x), None, n_heads, causal=True)
+        if cross:
+            x = x + mha(sd, prefix + "ca.", ln("ca_norm", x), memory, n_heads)
+        return x + mlp(sd, prefix + "mlp.", ln("mlp_norm", x), act)
+    x = ln("sa_norm", x + mha(sd, prefix + "sa.", x, None, n_heads, causal=True))
+    if cross:
+        x = ln("ca_norm", x + mha(sd, prefix + "ca.", x, memory, n_heads))
+    return ln("mlp_norm", x + mlp(sd, prefix + "mlp.", x, act))
+
+
+def decoder(sd: dict, x: Tensor, memory: Tensor | None, n_heads: int, pre_norm: bool, eps: float,
+            act: str = "gelu", prefix: str = "layers.") -> Tensor:
+    """Decoder.forward (transformer.py:173-176)."""
+    for i in range(n_layers_of(sd, prefix)):
+        x = decoder_layer(sd, f"{prefix}{i}.", x, memory, n_heads, pre_norm, eps, act)
+    return x
 
 
 def n_layers_of(sd: dict, prefix: str = "layers.") -> int:
@@ -106,6 +134,39 @@ def bert_forward(sd: dict, tokens: Tensor, eps: float = 1e-12) -> Tensor:
     return encoder(sd, x, x.shape[-1] // 64, False, eps)
 
 
+def sub_dict(sd: dict, prefix: str) -> dict:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def whisper_decoder_forward(sd: dict, tokens: Tensor, memory: Tensor, eps: float = 1e-5) -> Tensor:
+    """WhisperDecoder.forward (whisper.py:46-52): embeddings, Decoder(cross_attn=True), LayerNorm, tied logits."""
+    x = F.embedding(tokens, sd["token_embs.weight"]) + sd["pos_embs"][: tokens.shape[1]]
+    x = decoder(sd, x, memory, x.shape[-1] // 64, True, eps)
+    x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+    return x @ sd["token_embs.weight"].T
+
+
+def whisper_forward(sd: dict, x: Tensor, targets: Tensor) -> Tensor:
+    """Whisper.forward (whisper.py:62-63)."""
+    memory = whisper_encoder_forward(sub_dict(sd, "encoder."), x)
+    return whisper_decoder_forward(sub_dict(sd, "decoder."), targets, memory)
+
+
+def gpt2_forward(sd: dict, tokens: Tensor, eps: float = 1e-5) -> Tensor:
+    """GPT2.forward (gpt2.py:21-27): pre-norm causal Decoder with tanh-GELU, final LayerNorm, tied logits."""
+    x = F.embedding(tokens, sd["token_embs.weight"]) + sd["pos_embs"][: tokens.shape[-1]]
+    x = decoder(sd, x, None, x.shape[-1] // 64, True, eps, "approximate_gelu")
+    x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+    return x @ sd["token_embs.weight"].T
+
+
+def gpt_forward(sd: dict, tokens: Tensor, eps: float = 1e-5) -> Tensor:
+    """GPT.forward (gpt.py:24-29): post-norm causal Decoder with tanh-GELU, no final norm, tied logits."""
+    x = F.embedding(tokens, sd["token_embs.weight"]) + sd["pos_embs"][: tokens.shape[-1]]
+    x = decoder(sd, x, None, x.shape[-1] // 64, False, eps, "approximate_gelu")
+    return x @ sd["token_embs.weight"].T
+
+
 def randomize_(sd: dict, seed: int) -> dict:
     """Seeded noise into the tensors the reference zero/one-initialises (cls_token, pe, pos_embs, probe, LayerNorm
     affine: vit.py:65-66, whisper.py:24), so those code paths are exercised (SURVEY §8(d) recipe)."""
@@ -115,7 +176,7 @@ def randomize_(sd: dict, seed: int) -> dict:
             continue
         last = k.split(".")[-1]
         is_norm = "norm" in k.split(".")[-2] if "." in k else False
-        if k in ("cls_token", "pe", "pos_embs", "pooler.probe"):
+        if k in ("cls_token", "pe", "pos_embs", "pooler.probe") or k.endswith(".pos_embs"):
             v.copy_(0.02 * torch.randn(v.shape, generator=g))
         elif is_norm and last == "weight":
             v.copy_(1.0 + 0.1 * torch.randn(v.shape, generator=g))

@@ -13,6 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 
 LINEAR_GELU = 1
+LINEAR_GELU_TANH = 2
+ATTN_CAUSAL = 1
 LINEAR_DIRECT_STORE = 256
 DTYPE_BF16 = 0
 DTYPE_F32 = 1
@@ -54,6 +56,8 @@ _SIGNATURES = {
         c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "b200enc_patch_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200enc_cls_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p]),
+    "b200enc_embed_rows": (
+        c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200enc_time_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,3 +1,3 @@
-from .whisper import WhisperEncoder
+from .whisper import Whisper, WhisperDecoder, WhisperEncoder
 
-__all__ = ["WhisperEncoder"]
+__all__ = ["Whisper", "WhisperDecoder", "WhisperEncoder"]

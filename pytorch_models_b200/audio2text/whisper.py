@@ -1,10 +1,14 @@
-"""B200-native drop-in for ``WhisperEncoder`` (reference ``pytorch_models/audio2text/whisper.py:11-34``).
+"""B200-native drop-in for ``WhisperEncoder`` / ``WhisperDecoder`` / ``Whisper`` (reference
+``pytorch_models/audio2text/whisper.py:11-135``).
 
 Same constructor, ``state_dict`` keys (``stem.0/2``, ``pos_embs`` buffer, ``layers.*``, ``norm``) and call signature.
 The conv stem runs as two GEMMs on the same tcgen05 kernel as the linears: the log-mel input is rewritten once as
 zero-padded time-major rows, after which a k=3 convolution over time is a GEMM over an *overlapping* strided view
 (row t starts at element stride·t·C and is 3·C long), with GELU — and for the second conv the positional embedding —
 fused into the epilogue (whisper.py:16-21,30-31).
+
+The decoder is one gather kernel (token + position embedding), the ``Decoder`` stack with causal self-attention and
+cross-attention to the encoder output, and one GEMM against the tied token table with the final LayerNorm folded in.
 """
 from __future__ import annotations
 
@@ -14,7 +18,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
-from ..transformer import Encoder, _Packed, norm_vectors
+from ..transformer import Decoder, Encoder, TiedLogits, _as_tokens, _Packed, embed_tokens, norm_vectors
 
 
 class WhisperEncoder(nn.Module):
@@ -94,24 +98,107 @@ class WhisperEncoder(nn.Module):
     @torch.no_grad()
     def load_openai_state_dict(self, state_dict: dict) -> None:
         """Encoder half of an openai-whisper checkpoint (``model_state_dict``), cf. whisper.py:97-135."""
-        sd = {k[len("encoder."):]: v for k, v in state_dict.items() if k.startswith("encoder.")}
+        _load_openai(self, state_dict, "encoder")
 
-        def take(module, key: str) -> None:
-            module.weight.copy_(sd.pop(f"{key}.weight"))
-            if module.bias is not None:
-                module.bias.copy_(sd.pop(f"{key}.bias", 0))  # the key projection has no bias in the checkpoint
 
-        take(self.stem[0], "conv1")
-        take(self.stem[2], "conv2")
-        self.pos_embs.copy_(sd.pop("positional_embedding"))
-        for i, layer in enumerate(self.layers):
-            pre = f"blocks.{i}"
-            take(layer.sa.q_proj, f"{pre}.attn.query")
-            take(layer.sa.k_proj, f"{pre}.attn.key")
-            take(layer.sa.v_proj, f"{pre}.attn.value")
-            take(layer.sa.out_proj, f"{pre}.attn.out")
-            take(layer.sa_norm, f"{pre}.attn_ln")
-            take(layer.mlp.linear1, f"{pre}.mlp.0")
-            take(layer.mlp.linear2, f"{pre}.mlp.2")
-            take(layer.mlp_norm, f"{pre}.mlp_ln")
-        take(self.norm, "ln_post")
+def _load_openai(half: nn.Module, state_dict: dict, prefix: str) -> None:
+    """Copy the ``encoder.*`` or ``decoder.*`` entries of an openai-whisper ``model_state_dict`` into ``half``
+    (whisper.py:97-132). The key projections have no bias in the checkpoint: their bias is set to zero."""
+    sd = {k[len(prefix) + 1:]: v for k, v in state_dict.items() if k.startswith(prefix + ".")}
+
+    def take(module, key: str) -> None:
+        module.weight.copy_(sd.pop(f"{key}.weight"))
+        if module.bias is not None:
+            module.bias.copy_(sd.pop(f"{key}.bias", 0))
+
+    if prefix == "encoder":
+        take(half.stem[0], "conv1")
+        take(half.stem[2], "conv2")
+    else:
+        half.token_embs.weight.copy_(sd.pop("token_embedding.weight"))
+    half.pos_embs.copy_(sd.pop("positional_embedding"))
+    for i, layer in enumerate(half.layers):
+        pre = f"blocks.{i}"
+        for mha, norm, name in ((layer.sa, layer.sa_norm, "attn"), (layer.ca, layer.ca_norm, "cross_attn")):
+            if mha is None:
+                continue
+            take(mha.q_proj, f"{pre}.{name}.query")
+            take(mha.k_proj, f"{pre}.{name}.key")
+            take(mha.v_proj, f"{pre}.{name}.value")
+            take(mha.out_proj, f"{pre}.{name}.out")
+            take(norm, f"{pre}.{name}_ln")
+        take(layer.mlp.linear1, f"{pre}.mlp.0")
+        take(layer.mlp.linear2, f"{pre}.mlp.2")
+        take(layer.mlp_norm, f"{pre}.mlp_ln")
+    take(half.norm, "ln_post" if prefix == "encoder" else "ln")
+
+
+class WhisperDecoder(nn.Module):
+    """Reference ``WhisperDecoder`` (whisper.py:37-53)."""
+
+    max_seq_len = 448
+
+    def __init__(self, vocab_size: int, n_layers: int, d_model: int, dropout: float = 0.0) -> None:
+        super().__init__()
+        self.token_embs = nn.Embedding(vocab_size, d_model)
+        self.pos_embs = nn.Parameter(torch.zeros(self.max_seq_len, d_model))
+        self.layers = Decoder(n_layers, d_model, cross_attn=True, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self._logits = TiedLogits()
+
+    def forward(self, x: Tensor, memory: Tensor) -> Tensor:
+        """x: (N, L) int64 token ids, memory: (N, Lm, d) encoder output -> (N, L, vocab) logits (whisper.py:46-52)."""
+        out_dtype = self.token_embs.weight.dtype
+        d = self.token_embs.weight.shape[1]
+        m3, _ = _as_tokens(memory, d)
+        h, stats = self.layers.run(embed_tokens(x, self.token_embs, self.pos_embs), m3, final_stats=True)
+        logits = self._logits(h, self.token_embs, self.norm, stats)
+        logits = logits.reshape(*x.shape, logits.shape[-1])
+        return logits if out_dtype == torch.bfloat16 else logits.to(out_dtype)
+
+
+_OPENAI_SIZES = {
+    # tag: (n_layers, d_model, checkpoint hash) — whisper.py:66-78
+    "tiny": (4, 384, "65147644a518d12f04e32d6f3b26facc3f8dd46e5390956a9424a650c0ce22b9"),
+    "tiny.en": (4, 384, "d3dd57d32accea0b295c96e26691aa14d8822fac7d9d27d5dc00b4ca2826dd03"),
+    "base": (8, 512, "ed3a0b6b1c0edf879ad9b11b1af5a0e6ab5db9205f891f668f8b0e6c6326e34e"),
+    "base.en": (8, 512, "25a8566e1d0c1e2231d1c762132cd20e0f96a85d16145c3a00adf5d1ac670ead"),
+    "small": (12, 768, "9ecf779972d90ba49c06d968637d720dd632c55bbf19d441fb42bf17a411e794"),
+    "small.en": (12, 768, "f953ad0fd29cacd07d5a9eda5624af0f6bcf2258be67c92b79389873d91e0872"),
+    "medium": (24, 1024, "345ae4da62f9b3d59415adc60127b97c714f32e89e936602e85993674d08dcb1"),
+    "medium.en": (24, 1024, "d7440d1dc186f76616474e0ff0b3b6b879abc9d1a4926b7adfa41db2d497ab4f"),
+    "large-v1": (32, 1280, "e4b87e7e0bf463eb8e6956e646f1e277e901512310def2c24bf0e11bd3c28e9a"),
+    "large-v2": (32, 1280, "81f7c96c852ee8fc832187b0132e569d6c3065a3252ed18e56effd0b6a73e524"),
+    "large-v3": (32, 1280, "e5b1a55b89c1367dacf97e3e19bfd829a01529dbfdeefa8caeb59b3f1b81dadb"),
+}
+
+
+class Whisper(nn.Module):
+    """Reference ``Whisper`` (whisper.py:56-135): ``decoder(targets, encoder(x))``."""
+
+    def __init__(self, vocab_size: int, n_layers: int, d_model: int, n_mels: int = 80, dropout: float = 0.0) -> None:
+        super().__init__()
+        self.encoder = WhisperEncoder(n_layers, d_model, n_mels, dropout=dropout)
+        self.decoder = WhisperDecoder(vocab_size, n_layers, d_model, dropout=dropout)
+
+    def forward(self, x: Tensor, targets: Tensor) -> Tensor:
+        return self.decoder(targets, self.encoder(x))
+
+    @staticmethod
+    def from_openai(model_tag: str, *, pretrained: bool = False, **kwargs) -> "Whisper":
+        n_layers, d_model, ckpt_hash = _OPENAI_SIZES[model_tag]
+        if model_tag == "large-v3":
+            n_mels, vocab_size = 128, 51866
+        else:
+            n_mels, vocab_size = 80, 51864 if model_tag.endswith(".en") else 51865
+        m = Whisper(vocab_size, n_layers, d_model, n_mels, **kwargs)
+        if pretrained:  # needs network access
+            url = f"https://openaipublic.azureedge.net/main/whisper/models/{ckpt_hash}/{model_tag}.pt"
+            sd = torch.hub.load_state_dict_from_url(url, file_name=f"whisper_{model_tag}")["model_state_dict"]
+            m.load_openai_state_dict(sd)
+        return m
+
+    @torch.no_grad()
+    def load_openai_state_dict(self, state_dict: dict) -> None:
+        _load_openai(self.encoder, state_dict, "encoder")
+        _load_openai(self.decoder, state_dict, "decoder")

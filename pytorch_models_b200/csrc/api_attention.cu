@@ -51,7 +51,7 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_batch_stride = out_batch_stride;
   p.ldo = ldo;
-  (void)flags;
+  p.causal = (flags & B200ENC_ATTN_CAUSAL) ? 1 : 0;
 #ifdef ATT_TRACE
   p.trace = g_attention_trace;
 #else

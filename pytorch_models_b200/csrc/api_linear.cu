@@ -7,10 +7,10 @@ using namespace b200;
 
 namespace {
 
-template <int kCtas, bool kFold, bool kGelu, bool kRes, bool kTma, bool kStats>
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<kCtas, kFold, kGelu, kRes, kTma, kStats>;
+  auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats>;
   constexpr int kSmem = GemmSmem<kCtas>::kBytes;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   cudaLaunchConfig_t cfg = {};
@@ -29,31 +29,34 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   return 0;
 }
 
-template <int kCtas, bool kFold, bool kGelu, bool kRes>
+template <int kCtas, bool kFold, int kAct, bool kRes>
 int dispatch_store(bool tma, bool stats, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const GemmParams& p, int grid, cudaStream_t s) {
   if constexpr (kRes && !kFold) {
-    if (stats && tma) return launch_gemm<kCtas, kFold, kGelu, kRes, true, true>(ta, tb, tc, p, grid, s);
+    if (stats && tma) return launch_gemm<kCtas, kFold, kAct, kRes, true, true>(ta, tb, tc, p, grid, s);
   }
   if (stats) return set_error(-1, "b200enc_linear: stats_out needs a residual, non-folded, TMA-store epilogue");
   if constexpr (kCtas == 1) {
-    if (!tma) return launch_gemm<1, kFold, kGelu, kRes, false, false>(ta, tb, tc, p, grid, s);
+    if (!tma) return launch_gemm<1, kFold, kAct, kRes, false, false>(ta, tb, tc, p, grid, s);
   }
-  return launch_gemm<kCtas, kFold, kGelu, kRes, true, false>(ta, tb, tc, p, grid, s);
+  return launch_gemm<kCtas, kFold, kAct, kRes, true, false>(ta, tb, tc, p, grid, s);
 }
 
 template <int kCtas>
 int dispatch_epilogue(int sel, bool tma, bool stats, const CUtensorMap& ta, const CUtensorMap& tb,
                       const CUtensorMap& tc, const GemmParams& p, int grid, cudaStream_t s) {
   switch (sel) {
-    case 0: return dispatch_store<kCtas, false, false, false>(tma, stats, ta, tb, tc, p, grid, s);
-    case 1: return dispatch_store<kCtas, false, false, true>(tma, stats, ta, tb, tc, p, grid, s);
-    case 2: return dispatch_store<kCtas, false, true, false>(tma, stats, ta, tb, tc, p, grid, s);
-    case 3: return dispatch_store<kCtas, false, true, true>(tma, stats, ta, tb, tc, p, grid, s);
-    case 4: return dispatch_store<kCtas, true, false, false>(tma, stats, ta, tb, tc, p, grid, s);
-    case 5: return dispatch_store<kCtas, true, false, true>(tma, stats, ta, tb, tc, p, grid, s);
-    case 6: return dispatch_store<kCtas, true, true, false>(tma, stats, ta, tb, tc, p, grid, s);
-    default: return dispatch_store<kCtas, true, true, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 0: return dispatch_store<kCtas, false, 0, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 1: return dispatch_store<kCtas, false, 0, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 2: return dispatch_store<kCtas, false, 1, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 3: return dispatch_store<kCtas, false, 1, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 4: return dispatch_store<kCtas, true, 0, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 5: return dispatch_store<kCtas, true, 0, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 6: return dispatch_store<kCtas, true, 1, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 7: return dispatch_store<kCtas, true, 1, true>(tma, stats, ta, tb, tc, p, grid, s);
+    case 8: return dispatch_store<kCtas, false, 2, false>(tma, stats, ta, tb, tc, p, grid, s);   // tanh-GELU
+    case 12: return dispatch_store<kCtas, true, 2, false>(tma, stats, ta, tb, tc, p, grid, s);   // LN fold + tanh-GELU
+    default: return set_error(-1, "b200enc_linear: tanh-GELU cannot be combined with a residual");
   }
 }
 
@@ -85,6 +88,8 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   }
   const bool fold = a->colsum != nullptr;
   const bool gelu = (a->flags & B200ENC_LINEAR_GELU) != 0;
+  const bool gelu_tanh = (a->flags & B200ENC_LINEAR_GELU_TANH) != 0;
+  B200_CHECK_ARG(!(gelu && gelu_tanh), "b200enc_linear: GELU and GELU_TANH are mutually exclusive");
   const bool res = a->residual != nullptr;
   const bool tma_store = (a->flags & B200ENC_LINEAR_DIRECT_STORE) == 0;
   const bool stats = a->stats_out != nullptr;
@@ -131,7 +136,7 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const int slots = sm_count() / ctas;  // CTAs (or CTA pairs) resident at once: the kernel is persistent
   const int grid = int(total < slots ? total : slots) * ctas;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int sel = (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
+  const int sel = (gelu_tanh ? 8 : 0) | (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
   if (ctas == 2) return dispatch_epilogue<2>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
   return dispatch_epilogue<1>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
 }

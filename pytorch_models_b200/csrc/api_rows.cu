@@ -96,6 +96,27 @@ extern "C" int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, lon
   return 0;
 }
 
+extern "C" int b200enc_embed_rows(const long long* ids, long long rows, int L, const void* tok, const void* pos,
+                                  int dtype, int vocab, int d, void* out, void* stream) {
+  B200_CHECK_ARG(ids && tok && pos && out && rows >= 1 && L >= 1 && vocab >= 1, "b200enc_embed_rows: bad arguments");
+  B200_CHECK_ARG(d >= 8 && d % 8 == 0, "b200enc_embed_rows: d=%d must be a multiple of 8", d);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "b200enc_embed_rows: out must be 16-byte aligned");
+  const long long total = rows * (d / 8);
+  const unsigned grid = unsigned((total + 255) / 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out);
+  if (dtype == B200ENC_DTYPE_BF16)
+    embed_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ids, rows, L, reinterpret_cast<const __nv_bfloat16*>(tok),
+                                                          reinterpret_cast<const __nv_bfloat16*>(pos), vocab, d, dst);
+  else if (dtype == B200ENC_DTYPE_F32)
+    embed_rows_kernel<float><<<grid, 256, 0, s>>>(ids, rows, L, reinterpret_cast<const float*>(tok),
+                                                  reinterpret_cast<const float*>(pos), vocab, d, dst);
+  else
+    return set_error(-1, "b200enc_embed_rows: unsupported dtype %d", dtype);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, void* rows, void* stream) {
   B200_CHECK_ARG(x && rows && N >= 1 && C >= 1 && T >= 1, "b200enc_time_rows: bad arguments");
   dim3 grid((T + 31) / 32, (C + 31) / 32, N);

@@ -25,9 +25,6 @@ constexpr int ATT_HD = 64;
 constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int ATT_KV_STAGES = 3;
-#ifndef ATT_PIPELINED_LD
-#define ATT_PIPELINED_LD 0
-#endif
 constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
 constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
 constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
@@ -39,6 +36,7 @@ struct AttnParams {
   int n_qp;           // ceil(Lq / 256): query-tile pairs per (batch, head)
   int n_items;        // B * H * n_qp
   float scale_log2e;  // softmax scale * log2(e)
+  int causal;         // 1: key j attends only to queries i >= j (top-left aligned, as F.scaled_dot_product_attention)
   __nv_bfloat16* out; // [B, Lq, ldo] with head h at columns [64h, 64h+64)
   long long out_batch_stride;
   int ldo;
@@ -109,6 +107,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O buffers at t*256 + 128 and t*256 + 192
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
+  // K/V blocks a query tile has to visit: all of them, or with a causal mask only those up to its last row's diagonal
+  auto tile_blocks = [&](int item, int t) {
+    const int row0 = (item % p.n_qp) * 256 + t * ATT_BQ;
+    if (row0 >= p.Lq) return 0;
+    if (!p.causal) return n_kvb;
+    return min(p.Lkv - 1, row0 + ATT_BQ - 1) / ATT_BKV + 1;
+  };
+  auto item_blocks = [&](int item) { return max(tile_blocks(item, 0), tile_blocks(item, 1)); };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
@@ -128,7 +134,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (two) tma_load_3d(&tmQ, bar(Q_FULL + qb), sq + ATT_TILE_BYTES, h * ATT_HD, qp * 256 + ATT_BQ, b);
       }
       __syncwarp();
-      for (int j = 0; j < n_kvb; ++j) {
+      const int nb = item_blocks(item);
+      for (int j = 0; j < nb; ++j) {
         mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
@@ -153,10 +160,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       struct Blk {
         int item, j;
         uint32_t it, stage, phase;
-        bool two;
+        int nb0, nb1;  // blocks visited by query tile 0 / 1 of this item (0 = tile absent)
+      };
+      auto active = [&](const Blk& bl, int t) { return bl.j < (t == 0 ? bl.nb0 : bl.nb1); };
+      auto set_item = [&](Blk& bl) {
+        bl.nb0 = bl.item < p.n_items ? tile_blocks(bl.item, 0) : 0;
+        bl.nb1 = bl.item < p.n_items ? tile_blocks(bl.item, 1) : 0;
       };
       auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
-      auto is_two = [&](int item) { return (item % p.n_qp) * 256 + ATT_BQ < p.Lq; };
       auto issue_qk = [&](const Blk& bl, int t) {
         const uint32_t sq = sbase + ATT_SMEM_Q + (bl.it & 1u) * 2 * ATT_TILE_BYTES + t * ATT_TILE_BYTES;
         const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
@@ -200,9 +211,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
         }
         for (int t = t_first; t <= t_last; ++t)
-          if (t == 0 || bl.two) issue_qk(bl, t);
+          if (active(bl, t)) issue_qk(bl, t);
         // after the last score MMA that reads this item's Q tiles has been issued, hand the Q buffer back
-        if (t_last == 1 && bl.j == n_kvb - 1) {
+        if (t_last == 1 && bl.j == max(bl.nb0, bl.nb1) - 1) {
           if (elect_one()) umma_commit(bar(Q_EMPTY + (bl.it & 1u)));
           __syncwarp();
         }
@@ -212,25 +223,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           bl.stage = 0;
           bl.phase ^= 1u;
         }
-        if (++bl.j == n_kvb) {
+        if (++bl.j == max(bl.nb0, bl.nb1)) {
           bl.j = 0;
           bl.item += gridDim.x;
           ++bl.it;
-          bl.two = bl.item < p.n_items ? is_two(bl.item) : false;
+          set_item(bl);
         }
         return bl;
       };
 
-      Blk cur{int(blockIdx.x), 0, 0u, 0u, 0u, false};
+      Blk cur{int(blockIdx.x), 0, 0u, 0u, 0u, 0, 0};
       if (cur.item < p.n_items) {
-        cur.two = is_two(cur.item);
+        set_item(cur);
         start_block(cur, 0, 1);
         while (true) {
           const Blk nxt = advance(cur);
           const bool more = nxt.item < p.n_items;
-          issue_pv(cur, 0);
+          if (active(cur, 0)) issue_pv(cur, 0);
           if (more) start_block(nxt, 0, 0);
-          if (cur.two) issue_pv(cur, 1);
+          if (active(cur, 1)) issue_pv(cur, 1);
           if (more) start_block(nxt, 1, 1);
           if (elect_one()) umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
           __syncwarp();
@@ -255,7 +266,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int h = bh % p.H;
       const int b = bh / p.H;
       const int row0 = qp * 256 + t * ATT_BQ;
-      if (row0 >= p.Lq) continue;                         // tile not scheduled at all (mirrors `two` in the MMA warp)
+      const int nb = tile_blocks(item, t);
+      if (nb == 0) continue;                              // tile not scheduled at all (same rule as the MMA warp)
       const bool warp_live = row0 + qd * 32 < p.Lq;       // any valid row in this warp?
       const int qrow = row0 + r;
       float m = -INFINITY, l = 0.0f, alpha_prev = 0.0f;
@@ -278,72 +290,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       };
 
-      for (int j = 0; j < n_kvb; ++j, ++g) {
+      for (int j = 0; j < nb; ++j, ++g) {
         const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
         const int nchunks = (nvalid + 31) >> 5;
+        // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
+        const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
+        const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
         mbar_wait(bar(S_FULL + t), g & 1u);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
         float alpha = 0.0f;
-#if ATT_PIPELINED_LD
-        if (warp_live) {
-          // Both passes keep one tcgen05.ld in flight while the previous 32 columns are processed.
-          uint32_t v[2][32];
-          // pass 1: row maximum over the valid columns
-          float mx = -INFINITY;
-          tmem_ld32(tS, v[0]);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            if (ch < nchunks) {
-              tmem_wait_ld();
-              if (ch + 1 < nchunks) tmem_ld32(tS + (ch + 1) * 32, v[(ch + 1) & 1]);
-              else tmem_ld32(tS, v[(ch + 1) & 1]);  // first chunk of pass 2
-              if (ch * 32 + 32 <= nvalid) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[ch & 1][i]));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(v[ch & 1][i]) : -INFINITY);
-              }
-            }
-          }
-          const float m_new = fmaxf(m, mx);
-          alpha = fast_exp2((m - m_new) * c);
-          const float mc = m_new * c;
-          float lsum = 0.0f;
-          // pass 2: p = exp2(s*c - m*c), row sum, P -> packed bf16 over the S columns. Chunk ch of pass 2 sits in
-          // buffer (nchunks + ch) & 1 because pass 1 alternated the buffers nchunks times.
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            if (ch < nchunks) {
-              tmem_wait_ld();
-              // buffer parity must be a compile-time index: handle the two cases of nchunks parity explicitly
-              uint32_t pk[16];
-              const bool full = ch * 32 + 32 <= nvalid;
-              auto body = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
-                if (ch + 1 < nchunks) tmem_ld32(tS + (ch + 1) * 32, nxt);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  float p0 = fast_exp2(fmaf(__uint_as_float(cur[2 * i]), c, -mc));
-                  float p1 = fast_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), c, -mc));
-                  if (!full) {
-                    p0 = (ch * 32 + 2 * i < nvalid) ? p0 : 0.0f;
-                    p1 = (ch * 32 + 2 * i + 1 < nvalid) ? p1 : 0.0f;
-                  }
-                  lsum += p0 + p1;
-                  pk[i] = pack_bf16x2(p0, p1);
-                }
-              };
-              if ((nchunks + ch) & 1) body(v[1], v[0]); else body(v[0], v[1]);
-              tmem_st16(tS + ch * 16, pk);
-            }
-          }
-          tmem_wait_st();
-          l = l * alpha + lsum;
-          m = m_new;
-        }
-#else
         if (warp_live) {
           // pass 1: row maximum over the valid columns
           float mx = -INFINITY;
@@ -351,12 +307,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             uint32_t v[32];
             tmem_ld32(tS + ch * 32, v);
             tmem_wait_ld();
-            if (ch * 32 + 32 <= nvalid) {
+            if (!diag && ch * 32 + 32 <= nvalid) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < lim) ? __uint_as_float(v[i]) : -INFINITY);
             }
           }
           const float m_new = fmaxf(m, mx);
@@ -369,14 +325,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_ld32(tS + ch * 32, v);
             tmem_wait_ld();
             uint32_t pk[16];
-            const bool full = ch * 32 + 32 <= nvalid;
+            const bool full = !diag && ch * 32 + 32 <= nvalid;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
               float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
               if (!full) {
-                p0 = (ch * 32 + 2 * i < nvalid) ? p0 : 0.0f;
-                p1 = (ch * 32 + 2 * i + 1 < nvalid) ? p1 : 0.0f;
+                p0 = (ch * 32 + 2 * i < lim) ? p0 : 0.0f;
+                p1 = (ch * 32 + 2 * i + 1 < lim) ? p1 : 0.0f;
               }
               lsum += p0 + p1;
               pk[i] = pack_bf16x2(p0, p1);
@@ -387,7 +343,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           l = l * alpha + lsum;
           m = m_new;
         }
-#endif
         // O_FULL of the previous block must be observed BEFORE this block's P is published: once P_FULL(j) is
         // complete the tensor core may finish P.V(j) and flip O_FULL again, and a parity wait that is lapped by two
         // phase completions never returns. (The data of block j-1 is still safe afterwards: O is double-buffered.)

@@ -87,7 +87,19 @@ __device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
   return __ffma2_rn(s, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
-template <int kCtas, bool kFold, bool kGelu, bool kRes, bool kTmaStore, bool kStats>
+// tanh-GELU (nn.GELU(approximate="tanh"), transformer.py:62; GPT / GPT-2): 0.5x(1 + tanh(u)) = x / (1 + e^(-2u)),
+// u = sqrt(2/pi)(x + 0.044715 x^3); the exponent is evaluated in base 2: w = x(c1 + c3 x^2), c1 = -2 sqrt(2/pi) log2 e.
+// One MUFU.EX2 and one MUFU.RCP per element; x -> -inf gives x * 0 = -0, x -> +inf gives x * 1.
+__device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
+  const float2 t = __fmul2_rn(x, x);
+  const float2 g = __ffma2_rn(t, make_float2(-0.10294324f, -0.10294324f), make_float2(-2.3022082f, -2.3022082f));
+  const float2 w = __fmul2_rn(x, g);
+  const float2 den = __fadd2_rn(make_float2(fast_exp2(w.x), fast_exp2(w.y)), make_float2(1.0f, 1.0f));
+  return make_float2(x.x * __frcp_rn(den.x), x.y * __frcp_rn(den.y));
+}
+
+// kAct: 0 = none, 1 = erf-GELU, 2 = tanh-GELU
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -346,7 +358,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float2 cb2 = u == 0 ? make_float2(cb.x, cb.y) : make_float2(cb.z, cb.w);
             const float2 cs2 = u == 0 ? make_float2(cs.x, cs.y) : make_float2(cs.z, cs.w);
             x[u] = kFold ? __ffma2_rn(rstd2, a, __ffma2_rn(nmr2, cs2, cb2)) : __fadd2_rn(a, cb2);
-            if (kGelu) x[u] = gelu_erf_fast2(x[u]);
+            if (kAct == 1) x[u] = gelu_erf_fast2(x[u]);
+            if (kAct == 2) x[u] = gelu_tanh_fast2(x[u]);
             if (kRes) {
               const uint32_t rr = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + u];
               x[u] = __fadd2_rn(x[u], make_float2(bf16_lo(rr), bf16_hi(rr)));

@@ -57,6 +57,32 @@ cls_rows_kernel(const __nv_bfloat16* __restrict__ cls, int B, int d, __nv_bfloat
   tokens[(long long)b * batch_stride + c] = cls[c];
 }
 
+// Token + position embedding (text/bert.py:35-36, text/gpt2.py:22-23, audio2text/whisper.py:47-48):
+// out[r][:] = bf16(tok[ids[r]][:] + pos[r % L][:]); 8 columns per thread. An id outside [0, vocab) cannot raise from
+// device code, so its row is filled with NaN instead of reading out of bounds.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+embed_rows_kernel(const long long* __restrict__ ids, long long rows, int L, const TIn* __restrict__ tok,
+                  const TIn* __restrict__ pos, int vocab, int d, __nv_bfloat16* __restrict__ out) {
+  const int vec_per_row = d >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * vec_per_row) return;
+  const long long r = t / vec_per_row;
+  const int c = int(t % vec_per_row) * 8;
+  const long long id = ids[r];
+  const bool ok = id >= 0 && id < vocab;
+  const TIn* trow = tok + (ok ? id : 0) * (long long)d + c;
+  const TIn* prow = pos + (long long)(r % L) * d + c;
+  uint32_t packed[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = ok ? float(trow[2 * i]) + float(prow[2 * i]) : __int_as_float(0x7fc00000);
+    const float b = ok ? float(trow[2 * i + 1]) + float(prow[2 * i + 1]) : __int_as_float(0x7fc00000);
+    packed[i] = pack_bf16x2(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + r * d + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 // Whisper stem input (audio2text/whisper.py:16-21,30): x (N, C, T) channel-major -> rows (N, T+2, C) time-major bf16,
 // rows 0 and T+1 zero. A k=3, pad=1 Conv1d over time then reads, for output step t, the 3*C contiguous values that
 // start at row t (stride 1) or 2t (stride 2): the convolution becomes a plain GEMM over an overlapping strided view.

@@ -83,6 +83,7 @@ static std::vector<float> rand_f32(size_t n, float scale) {
 }
 
 static double gelu_ref(double x) { return 0.5 * x * (1.0 + erf(x / sqrt(2.0))); }
+static double gelu_tanh_ref(double x) { return 0.5 * x * (1.0 + tanh(0.7978845608028654 * (x + 0.044715 * x * x * x))); }
 
 struct CmpStat {
   double max_abs = 0, max_rel = 0;
@@ -124,7 +125,9 @@ static bool report(const char* name, const CmpStat& st) {
 struct LinearCase {
   const char* name;
   int batches, M, N, K;
-  bool fold, gelu, res, res_bcast, direct, ints;
+  bool fold;
+  int gelu;  // 0 none, 1 erf, 2 tanh
+  bool res, res_bcast, direct, ints;
   int out_row_off;  // output rows shifted by this inside a (M + off)-row batch (patch-embed layout)
   int check_rows;   // rows per batch checked on the CPU (0 = all)
   int time_iters;
@@ -166,7 +169,7 @@ static bool run_linear(const LinearCase& c) {
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));  // sentinel 0x7f7f = 3.39e38 in bf16
 
   const int dbg = getenv("B200_DEBUG_FLAGS") ? atoi(getenv("B200_DEBUG_FLAGS")) : 0;  // timing experiments only
-  const int flags = (c.gelu ? B200ENC_LINEAR_GELU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
+  const int flags = (c.gelu == 1 ? B200ENC_LINEAR_GELU : c.gelu == 2 ? B200ENC_LINEAR_GELU_TANH : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
   const int n_slices = (N + 127) / 128;
   const bool want_stats = c.res && !c.fold && !c.direct;
   GuardedBuf gso(size_t(B) * M * n_slices * 8);
@@ -217,7 +220,8 @@ static bool run_linear(const LinearCase& c) {
         } else {
           v = acc + hb[n];
         }
-        if (c.gelu) v = gelu_ref(v);
+        if (c.gelu == 1) v = gelu_ref(v);
+        if (c.gelu == 2) v = gelu_tanh_ref(v);
         if (c.res) v += bf2f(hr[(c.res_bcast ? size_t(m) : size_t(b) * M + m) * N + n]);
         const float got = bf2f(ho[(size_t(b) * Mo + c.out_row_off + m) * N + n]);
         cmp_one(st, v, got, c.ints ? 1e-6 : 0.02, c.ints ? 0.0 : 0.01, b * M + m, n, c.name);
@@ -288,6 +292,8 @@ static const LinearCase kLinearCases[] = {
     {"many_tiles", 1, 19000, 768, 768, false, false, false, false, false, false, 0, 40, 0},
     {"embed_like", 3, 196, 768, 768, false, false, true, true, false, false, 1, 0, 0},
     {"fold_gelu", 1, 1000, 3072, 768, true, true, false, false, false, false, 0, 60, 0},
+    {"fold_gelu_tanh", 1, 1000, 3072, 768, true, 2, false, false, false, false, 0, 60, 0},
+    {"gelu_tanh", 2, 300, 512, 256, false, 2, false, false, false, false, 0, 60, 0},
     {"residual", 1, 1000, 768, 3072, false, false, true, false, false, false, 0, 60, 0},
     {"fold_qkv", 1, 1000, 2304, 768, true, false, false, false, false, false, 0, 60, 0},
     {"perf_qkv", 1, 25216, 2304, 768, true, false, false, false, false, false, 0, 16, 20},
@@ -307,15 +313,15 @@ struct AttnCase {
   const char* name;
   int B, H, Lq, Lkv;
   bool self_qkv;  // q/k/v are slices of one fused [B, L, 3*H*64] buffer
-  bool p_smem;
+  bool causal;
   float mag;
   int check_bh;  // number of (b,h) pairs checked (0 = all)
   int time_iters;
 };
 
 static bool run_attn(const AttnCase& c) {
-  printf("attention %s: B=%d H=%d Lq=%d Lkv=%d self=%d p_smem=%d\n", c.name, c.B, c.H, c.Lq, c.Lkv, c.self_qkv,
-         c.p_smem);
+  printf("attention %s: B=%d H=%d Lq=%d Lkv=%d self=%d causal=%d\n", c.name, c.B, c.H, c.Lq, c.Lkv, c.self_qkv,
+         c.causal);
   fflush(stdout);
   const int B = c.B, H = c.H, Lq = c.Lq, Lkv = c.Lkv, D = H * 64;
   std::vector<uint16_t> hq, hkv;
@@ -346,7 +352,7 @@ static bool run_attn(const AttnCase& c) {
   auto call = [&]() {
     return b200enc_attention(dq.p, (long long)Lq * ldq, ldq, kvbase_d + koff, kvbase_d + voff, (long long)Lkv * ldkv,
                              ldkv, dout.p, (long long)Lq * D, D, B, H, Lq, Lkv, 64, scale,
-                             0, nullptr);
+                             c.causal ? B200ENC_ATTN_CAUSAL : 0, nullptr);
   };
   int rc = call();
   if (rc) {
@@ -369,7 +375,8 @@ static bool run_attn(const AttnCase& c) {
     for (int i = 0; i < Lq; ++i) {
       const uint16_t* qr = &hq[(size_t(b) * Lq + i) * ldq + h * 64];
       double mx = -1e300;
-      for (int j = 0; j < Lkv; ++j) {
+      const int jmax = c.causal ? std::min(Lkv, i + 1) : Lkv;
+      for (int j = 0; j < jmax; ++j) {
         const uint16_t* kr = kvbase_h + (size_t(b) * Lkv + j) * ldkv + koff + h * 64;
         double a = 0;
         for (int t = 0; t < 64; ++t) a += double(bf2f(qr[t])) * double(bf2f(kr[t]));
@@ -378,7 +385,7 @@ static bool run_attn(const AttnCase& c) {
       }
       double den = 0;
       for (int j = 0; j < Lkv; ++j) {
-        sc[j] = exp(sc[j] - mx);
+        sc[j] = j < jmax ? exp(sc[j] - mx) : 0.0;
         den += sc[j];
       }
       for (int t = 0; t < 64; ++t) {
@@ -425,6 +432,12 @@ static const AttnCase kAttnCases[] = {
     {"l1370_tmem", 1, 2, 1370, 1370, true, false, 3.0f, 1, 0},
     {"cross_q1", 3, 2, 1, 576, false, false, 2.0f, 0, 0},
     {"l16", 3, 2, 16, 16, true, false, 2.0f, 0, 0},
+    {"causal_l16", 3, 2, 16, 16, true, true, 2.0f, 0, 0},
+    {"causal_l197", 2, 3, 197, 197, true, true, 2.0f, 0, 0},
+    {"causal_l448", 2, 2, 448, 448, true, true, 2.0f, 0, 0},
+    {"causal_l700", 1, 2, 700, 700, true, true, 2.0f, 0, 0},
+    {"causal_many", 30, 6, 300, 300, true, true, 2.0f, 8, 0},
+    {"perf_causal_1500", 8, 20, 1500, 1500, true, true, 1.0f, 1, 10},
     {"l130", 2, 2, 130, 130, true, false, 2.0f, 0, 0},
     {"l256", 2, 2, 256, 256, true, false, 2.0f, 0, 0},
     {"cross_q300_kv200", 2, 2, 300, 200, false, false, 2.0f, 0, 0},

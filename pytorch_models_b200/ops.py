@@ -71,13 +71,14 @@ def linear(
     colsum: Tensor | None = None,
     rowstats: Tensor | None = None,
     residual: Tensor | None = None,
-    gelu: bool = False,
+    gelu: bool | str = False,
     direct_store: bool = False,
     ln_eps: float = 0.0,
     stats_out: Tensor | None = None,
 ) -> Tensor:
     """out[b, m, :] = epilogue(x[b, m, :] @ w.T); x, out, residual are (batches, M, *) views with unit inner stride.
 
+    ``gelu``: False, True (exact erf form) or "tanh" (``nn.GELU(approximate="tanh")``; not with a residual).
     A residual with a leading dimension of 1 is broadcast over the batch (positional embedding).
     ``rowstats`` is either (batches*M, 2) = (mean, rstd) from `row_stats`, or (batches*M, parts, 2) partial
     (mean, M2) per 128 input columns as written through ``stats_out`` by the linear that produced ``x``
@@ -110,7 +111,10 @@ def linear(
         parts = 0 if rowstats.dim() == 2 else rowstats.shape[1]
     if stats_out is not None and (not stats_out.is_contiguous() or stats_out.numel() != 2 * batches * M * ((N + 127) // 128)):
         raise ValueError("stats_out must be a contiguous (batches*M, ceil(N/128), 2) tensor")
-    flags = (_lib.LINEAR_GELU if gelu else 0) | (_lib.LINEAR_DIRECT_STORE if direct_store else 0)
+    if gelu not in (False, True, "tanh"):
+        raise ValueError(f"gelu must be False, True or 'tanh', got {gelu!r}")
+    act = _lib.LINEAR_GELU_TANH if gelu == "tanh" else (_lib.LINEAR_GELU if gelu else 0)
+    flags = act | (_lib.LINEAR_DIRECT_STORE if direct_store else 0)
     args = _lib.LinearArgs(
         x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum),
         _ptr(rowstats), parts, float(ln_eps), _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1),
@@ -123,8 +127,10 @@ def linear(
     return out
 
 
-def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float) -> Tensor:
-    """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64)."""
+def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, causal: bool = False) -> Tensor:
+    """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64).
+
+    ``causal``: query i sees keys 0..i (top-left aligned like ``F.scaled_dot_product_attention(is_causal=True)``)."""
     _need_cuda(q, k, v, out)
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, name)
@@ -137,10 +143,10 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
     if k.shape != v.shape or k.stride() != v.stride() or k.shape[0] != B or k.shape[2] != D or out.shape != q.shape:
         raise ValueError("q/k/v/out shapes or strides are inconsistent")
     _call(
-        "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv),
+        "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal)),
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),
         out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
-        0, _stream(),
+        _lib.ATTN_CAUSAL if causal else 0, _stream(),
     )
     return out
 
@@ -238,3 +244,31 @@ def time_rows(x: Tensor, rows: Tensor) -> Tensor:
         x.data_ptr(), dt, N, C, T, rows.data_ptr(), _stream()
     )
     return rows
+
+
+def embed_rows(ids: Tensor, tok: Tensor, pos: Tensor, out: Tensor) -> Tensor:
+    """ids: (B, L) int64, tok: (vocab, d), pos: (>= L, d) [both fp32 or both bf16] -> out (B, L, d) bf16 =
+    tok[ids] + pos[:L]. Rows whose id is out of range come back as NaN (device code cannot raise)."""
+    _need_cuda(ids, tok, pos, out)
+    _need(ids, torch.int64, "ids"), _need(out, torch.bfloat16, "out")
+    if tok.dtype != pos.dtype:
+        raise TypeError(f"token and position tables must share a dtype, got {tok.dtype} and {pos.dtype}")
+    if tok.dtype == torch.bfloat16:
+        dt = _lib.DTYPE_BF16
+    elif tok.dtype == torch.float32:
+        dt = _lib.DTYPE_F32
+    else:
+        raise TypeError(f"embedding tables must be bfloat16 or float32, got {tok.dtype}")
+    if ids.dim() != 2 or not (ids.is_contiguous() and tok.is_contiguous() and pos.is_contiguous() and out.is_contiguous()):
+        raise ValueError("embed_rows expects contiguous (B, L) ids, (vocab, d) / (P, d) tables and (B, L, d) output")
+    B, L = ids.shape
+    vocab, d = tok.shape
+    if pos.shape[1] != d or pos.shape[0] < L or out.shape != (B, L, d):
+        raise ValueError(f"shape mismatch: ids {tuple(ids.shape)}, tok {tuple(tok.shape)}, pos {tuple(pos.shape)}")
+    if B * L == 0:
+        return out
+    _call(
+        "b200enc_embed_rows", None,
+        ids.data_ptr(), B * L, L, tok.data_ptr(), pos.data_ptr(), dt, vocab, d, out.data_ptr(), _stream()
+    )
+    return out

@@ -12,7 +12,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
-from ..transformer import Encoder, norm_vectors
+from ..transformer import Encoder, embed_tokens, norm_vectors
 
 
 class BERT(nn.Module):
@@ -33,13 +33,9 @@ class BERT(nn.Module):
         self.layers = Encoder(n_layers, d_model, dropout=dropout, pre_norm=False, norm_eps=norm_eps)
 
     def forward(self, x: Tensor) -> Tensor:
-        if not x.is_cuda:
-            raise RuntimeError("pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")
         out_dtype = self.token_embs.weight.dtype
-        L = x.shape[-1]
-        emb = (self.token_embs(x) + self.pos_embs[:L]).to(torch.bfloat16)
-        emb3 = emb.reshape(-1, L, emb.shape[-1]).contiguous()
-        B, _, d = emb3.shape
+        emb3 = embed_tokens(x, self.token_embs, self.pos_embs)
+        B, L, d = emb3.shape
         gamma, beta = norm_vectors(self.norm)
         h = torch.empty_like(emb3)
         ops.layernorm(emb3.view(B * L, d), gamma, beta, self.norm.eps, h.view(B * L, d))

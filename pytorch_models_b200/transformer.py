@@ -1,4 +1,4 @@
-"""B200-native drop-in for the encoder half of ``pytorch_models/transformer.py`` (reference lines cited inline).
+"""B200-native drop-in for ``pytorch_models/transformer.py`` (reference lines cited inline).
 
 Same class names, constructor signatures, attribute names and ``state_dict`` keys as the reference, so
 ``new.load_state_dict(ref.state_dict())`` is strict-clean and the reference's weight loaders (which write in place
@@ -16,7 +16,8 @@ hand-written sm_100a kernels from ``libb200enc.so``:
     its input (per-128-column (mean, M2) partials, combined in a fixed order by the consumer), so no separate pass
     over the residual stream is needed after the first layer.
 
-Only what the kernels implement is accepted (self/cross attention without mask, head_dim 64, exact GELU, eval mode);
+Only what the kernels implement is accepted (self/cross attention, optionally causal, no attn_bias; head_dim 64;
+erf or tanh GELU; eval mode);
 anything else raises ``NotImplementedError`` — there is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -143,8 +144,6 @@ class MHA(nn.Module):
     def check_supported(self, attn_bias: Tensor | None = None, causal: bool = False) -> None:
         if attn_bias is not None:
             raise NotImplementedError("attn_bias is not supported by the sm_100a attention kernel")
-        if causal:
-            raise NotImplementedError("causal attention is not supported by the sm_100a attention kernel")
         if self.head_dim != _SUPPORTED_HEAD_DIM:
             raise NotImplementedError(f"head_dim={self.head_dim}: the sm_100a attention kernel is specialised on 64")
         if self.training and self.dropout > 0.0:
@@ -197,7 +196,7 @@ class MHA(nn.Module):
                 qv = qv.expand(Bk, Lq, inner).contiguous()
                 B = Bk
         att = torch.empty(B, Lq, inner, device=dev, dtype=torch.bfloat16)
-        ops.attention(qv, kv_k, kv_v, att, self.n_heads, self.scale)
+        ops.attention(qv, kv_k, kv_v, att, self.n_heads, self.scale, causal)
         po = self._pack("out", [self.out_proj])
         out = torch.empty(B, Lq, self.out_proj.out_features, device=dev, dtype=torch.bfloat16)
         ops.linear(att.view(B * Lq, inner), po.w, po.bias, out.view(B * Lq, -1))
@@ -227,10 +226,16 @@ class MLP(nn.Sequential):
         self._p1, self._p2 = _Packed(), _Packed()
 
     def check_supported(self) -> None:
-        if self._act_name != "gelu":
-            raise NotImplementedError(f"act={self._act_name!r}: only exact (erf) GELU is fused into the sm_100a GEMM epilogue")
+        if self._act_name not in ("gelu", "approximate_gelu"):
+            raise NotImplementedError(
+                f"act={self._act_name!r}: only GELU (exact erf or tanh form) is fused into the sm_100a GEMM epilogue")
         if self.training and self.dropout.p > 0.0:
             raise NotImplementedError("MLP dropout (training mode) is not supported; call .eval()")
+
+    @property
+    def gelu_mode(self) -> bool | str:
+        """Epilogue selector of `ops.linear`: exact erf GELU, or the tanh form for ``act="approximate_gelu"``."""
+        return "tanh" if self._act_name == "approximate_gelu" else True
 
     def pack1(self, norm: nn.LayerNorm | None) -> SimpleNamespace:
         lin = self.linear1
@@ -250,14 +255,179 @@ class MLP(nn.Sequential):
         p1, p2 = self.pack1(None), self.pack2()
         hidden = torch.empty(B * L, self.linear1.out_features, device=x3.device, dtype=torch.bfloat16)
         out = torch.empty(B, L, d, device=x3.device, dtype=torch.bfloat16)
-        ops.linear(x3.view(B * L, d), p1.w, p1.bias, hidden, gelu=True)
+        ops.linear(x3.view(B * L, d), p1.w, p1.bias, hidden, gelu=self.gelu_mode)
         ops.linear(hidden, p2.w, p2.bias, out.view(B * L, d))
         y = _restore(out, meta)
         return y.squeeze(0) if x.dim() == 2 else y
 
 
-class EncoderLayer(nn.Module):
-    """Reference ``EncoderLayer`` (transformer.py:108-130; fields created at :84-94 with ``cross_attn=False``)."""
+class DecoderLayer(nn.Module):
+    """Reference ``DecoderLayer`` (transformer.py:70-105): causal self-attention, optional cross-attention to an
+    encoder ``memory``, MLP; pre-norm (:97-99) or post-norm (:101-103). ``EncoderLayer`` is the same sequence without
+    the mask and without cross-attention, exactly as in the reference (transformer.py:108).
+
+    Launch sequence, pre-norm (one row per launch; LayerNorms never run as separate passes):
+        linear [3·inner, d], sa_norm folded        -> q|k|v
+        attention (causal for the decoder)         -> att
+        linear sa.out_proj + bias + x              -> x1, partial statistics of x1
+        [cross-attention only]
+        linear ca.q_proj, ca_norm folded (on x1)   -> qc
+        linear [ca.k_proj; ca.v_proj] on memory    -> k|v of the memory (memory is not normalised, :98)
+        attention                                  -> att
+        linear ca.out_proj + bias + x1             -> x2, partial statistics of x2
+        linear1, mlp_norm folded, GELU             -> hidden
+        linear2 + bias + x2                        -> out, partial statistics of out for the next layer
+    """
+
+    _causal = True
+
+    def __init__(
+        self,
+        d_model: int,
+        n_heads: int | None = None,
+        head_dim: int | None = None,
+        cross_attn: bool = False,
+        bias: bool = True,
+        mlp_ratio: float = 4.0,
+        dropout: float = 0.0,
+        act: str = "gelu",
+        pre_norm: bool = True,
+        norm_eps: float = 1e-5,
+    ) -> None:
+        super().__init__()
+        self.pre_norm = pre_norm
+        self.sa_norm = nn.LayerNorm(d_model, norm_eps)
+        self.sa = MHA(d_model, n_heads, head_dim, bias, dropout)
+        self.ca_norm = nn.LayerNorm(d_model, norm_eps) if cross_attn else None
+        self.ca = MHA(d_model, n_heads, head_dim, bias, dropout) if cross_attn else None
+        self.mlp_norm = nn.LayerNorm(d_model, norm_eps)
+        self.mlp = MLP(d_model, int(d_model * mlp_ratio), dropout, act)
+        self._pqkv, self._pcq = _Packed(), _Packed()
+
+    # -- packing -------------------------------------------------------------------------------
+    def _pack_proj(self, slot: _Packed, lins: list[nn.Linear], norm: nn.LayerNorm) -> SimpleNamespace:
+        params = tuple(p for lin in lins for p in (lin.weight, lin.bias))
+        if self.pre_norm:
+            return slot.get(params + (norm.weight, norm.bias), lambda: pack_folded(lins, norm))
+        return slot.get(params, lambda: pack_plain(lins))
+
+    def _pack_qkv(self) -> SimpleNamespace:
+        sa = self.sa
+        return self._pack_proj(self._pqkv, [sa.q_proj, sa.k_proj, sa.v_proj], self.sa_norm)
+
+    def workspace(self, B: int, L: int, device: torch.device, Lm: int = 0) -> SimpleNamespace:
+        d = self.sa_norm.normalized_shape[0]
+        inner = self.sa.n_heads * self.sa.head_dim
+        M = B * L
+        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        parts = (d + 127) // 128
+        fused = self.pre_norm and parts <= _MAX_STAT_PARTS
+        ws = SimpleNamespace(
+            qkv=e(B, L, 3 * inner), att=e(B, L, inner), hidden=e(M, self.mlp.linear1.out_features), mid=e(M, d),
+            tmp=None if self.pre_norm else e(M, d), stats=e(M, 2, dt=torch.float32),
+            parts_mid=e(M, parts, 2, dt=torch.float32) if fused else None,
+            parts_out=e(M, parts, 2, dt=torch.float32) if fused else None,
+            Lm=Lm,
+        )
+        if self.ca is not None:
+            ci = self.ca.n_heads * self.ca.head_dim
+            ws.cq, ws.ckv, ws.catt, ws.mid2 = e(B, L, ci), e(B, Lm, 2 * ci), e(B, L, ci), e(M, d)
+            ws.parts_mid2 = e(M, parts, 2, dt=torch.float32) if fused else None
+        return ws
+
+    def run(self, x3: Tensor, out3: Tensor, ws: SimpleNamespace, stats_in: Tensor | None = None,
+            want_stats: bool = False, memory3: Tensor | None = None) -> Tensor | None:
+        """x3 (B, L, d) bf16 contiguous -> out3 (same shape, must not alias x3); memory3 (B, Lm, d) bf16 contiguous.
+
+        ``stats_in``: partial LayerNorm statistics of x3 written by the producing GEMM (else a row_stats pass runs).
+        Returns the partial statistics of out3 when ``want_stats`` (for the next layer's sa_norm), else None."""
+        sa, ca, mlp = self.sa, self.ca, self.mlp
+        sa.check_supported()
+        mlp.check_supported()
+        B, L, d = x3.shape
+        M = B * L
+        inner = sa.n_heads * sa.head_dim
+        x2, out2 = x3.view(M, d), out3.view(M, d)
+        pq = self._pack_qkv()
+        po = sa._pack("out", [sa.out_proj])
+        p1 = mlp.pack1(self.mlp_norm if self.pre_norm else None)
+        p2 = mlp.pack2()
+        qkv2 = ws.qkv.view(M, 3 * inner)
+        q, k, v = ws.qkv[:, :, :inner], ws.qkv[:, :, inner:2 * inner], ws.qkv[:, :, 2 * inner:]
+        if ca is not None:
+            ca.check_supported()
+            if memory3 is None:
+                raise ValueError("a DecoderLayer built with cross_attn=True needs `memory`")
+            if memory3.shape[0] != B or memory3.shape[2] != d or memory3.shape[1] != ws.Lm:
+                raise ValueError(f"memory {tuple(memory3.shape)} does not match the workspace / batch")
+            ci = ca.n_heads * ca.head_dim
+            Mm = B * ws.Lm
+            pcq = self._pack_proj(self._pcq, [ca.q_proj], self.ca_norm)
+            pckv = ca._pack("kv", [ca.k_proj, ca.v_proj])
+            pco = ca._pack("out", [ca.out_proj])
+            ck, cv = ws.ckv[:, :, :ci], ws.ckv[:, :, ci:]
+        if self.pre_norm:
+            if stats_in is None:
+                stats_in = ops.row_stats(x2, self.sa_norm.eps, ws.stats)
+            ops.linear(x2, pq.w, pq.bias, qkv2, colsum=pq.colsum, rowstats=stats_in, ln_eps=self.sa_norm.eps)
+            ops.attention(q, k, v, ws.att, sa.n_heads, sa.scale, self._causal)
+            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.mid, residual=x2, stats_out=ws.parts_mid)
+            mid, mid_stats = ws.mid, ws.parts_mid
+            if ca is not None:
+                if mid_stats is None:
+                    mid_stats = ops.row_stats(mid, self.ca_norm.eps, ws.stats)
+                ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci), colsum=pcq.colsum, rowstats=mid_stats,
+                           ln_eps=self.ca_norm.eps)
+                ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
+                ops.attention(ws.cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
+                ops.linear(ws.catt.view(M, ci), pco.w, pco.bias, ws.mid2, residual=mid, stats_out=ws.parts_mid2)
+                mid, mid_stats = ws.mid2, ws.parts_mid2
+            if mid_stats is None:
+                mid_stats = ops.row_stats(mid, self.mlp_norm.eps, ws.stats)
+            ops.linear(mid, p1.w, p1.bias, ws.hidden, colsum=p1.colsum, rowstats=mid_stats,
+                       ln_eps=self.mlp_norm.eps, gelu=mlp.gelu_mode)
+            out_stats = ws.parts_out if want_stats else None
+            ops.linear(ws.hidden, p2.w, p2.bias, out2, residual=mid, stats_out=out_stats)
+            return out_stats
+        else:  # post-norm (BERT, GPT): transformer.py:101-103,128-129
+            g1, b1 = norm_vectors(self.sa_norm)
+            g2, b2 = norm_vectors(self.mlp_norm)
+            ops.linear(x2, pq.w, pq.bias, qkv2)
+            ops.attention(q, k, v, ws.att, sa.n_heads, sa.scale, self._causal)
+            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.tmp, residual=x2)
+            ops.layernorm(ws.tmp, g1, b1, self.sa_norm.eps, ws.mid)
+            mid = ws.mid
+            if ca is not None:
+                gc, bc = norm_vectors(self.ca_norm)
+                ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci))
+                ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
+                ops.attention(ws.cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
+                ops.linear(ws.catt.view(M, ci), pco.w, pco.bias, ws.tmp, residual=mid)
+                ops.layernorm(ws.tmp, gc, bc, self.ca_norm.eps, ws.mid2)
+                mid = ws.mid2
+            ops.linear(mid, p1.w, p1.bias, ws.hidden, gelu=mlp.gelu_mode)
+            ops.linear(ws.hidden, p2.w, p2.bias, ws.tmp, residual=mid)
+            ops.layernorm(ws.tmp, g2, b2, self.mlp_norm.eps, out2)
+        return None
+
+    def forward(self, x: Tensor, memory: Tensor | None = None) -> Tensor:
+        d = self.sa_norm.normalized_shape[0]
+        x3, meta = _as_tokens(x, d)
+        m3 = None
+        if self.ca is not None and memory is not None:
+            m3, _ = _as_tokens(memory, d)
+        out3 = torch.empty_like(x3)
+        if x3.numel():
+            ws = self.workspace(x3.shape[0], x3.shape[1], x3.device, 0 if m3 is None else m3.shape[1])
+            self.run(x3, out3, ws, memory3=m3)
+        return _restore(out3, meta)
+
+
+class EncoderLayer(DecoderLayer):
+    """Reference ``EncoderLayer`` (transformer.py:108-130): a ``DecoderLayer`` without cross-attention whose
+    self-attention is not masked."""
+
+    _causal = False
 
     def __init__(
         self,
@@ -271,91 +441,10 @@ class EncoderLayer(nn.Module):
         pre_norm: bool = True,
         norm_eps: float = 1e-5,
     ) -> None:
-        super().__init__()
-        self.pre_norm = pre_norm
-        self.sa_norm = nn.LayerNorm(d_model, norm_eps)
-        self.sa = MHA(d_model, n_heads, head_dim, bias, dropout)
-        self.ca_norm = None  # attribute kept for parity with the reference's DecoderLayer base (transformer.py:90-91)
-        self.ca = None
-        self.mlp_norm = nn.LayerNorm(d_model, norm_eps)
-        self.mlp = MLP(d_model, int(d_model * mlp_ratio), dropout, act)
-        self._pqkv = _Packed()
-
-    # -- packing -------------------------------------------------------------------------------
-    def _pack_qkv(self) -> SimpleNamespace:
-        sa = self.sa
-        lins = [sa.q_proj, sa.k_proj, sa.v_proj]
-        params = tuple(p for lin in lins for p in (lin.weight, lin.bias))
-        if self.pre_norm:
-            params += (self.sa_norm.weight, self.sa_norm.bias)
-            return self._pqkv.get(params, lambda: pack_folded(lins, self.sa_norm))
-        return self._pqkv.get(params, lambda: pack_plain(lins))
-
-    def workspace(self, B: int, L: int, device: torch.device) -> SimpleNamespace:
-        d = self.sa_norm.normalized_shape[0]
-        inner = self.sa.n_heads * self.sa.head_dim
-        M = B * L
-        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
-        parts = (d + 127) // 128
-        fused = self.pre_norm and parts <= _MAX_STAT_PARTS
-        return SimpleNamespace(
-            qkv=e(B, L, 3 * inner), att=e(B, L, inner), hidden=e(M, self.mlp.linear1.out_features), mid=e(M, d),
-            tmp=None if self.pre_norm else e(M, d), stats=e(M, 2, dt=torch.float32),
-            parts_mid=e(M, parts, 2, dt=torch.float32) if fused else None,
-            parts_out=e(M, parts, 2, dt=torch.float32) if fused else None,
-        )
-
-    def run(self, x3: Tensor, out3: Tensor, ws: SimpleNamespace, stats_in: Tensor | None = None,
-            want_stats: bool = False) -> Tensor | None:
-        """x3 (B, L, d) bf16 contiguous -> out3 (same shape, must not alias x3).
-
-        ``stats_in``: partial LayerNorm statistics of x3 written by the producing GEMM (else a row_stats pass runs).
-        Returns the partial statistics of out3 when ``want_stats`` (for the next layer's sa_norm), else None."""
-        sa, mlp = self.sa, self.mlp
-        sa.check_supported()
-        mlp.check_supported()
-        B, L, d = x3.shape
-        M = B * L
-        inner = sa.n_heads * sa.head_dim
-        x2, out2 = x3.view(M, d), out3.view(M, d)
-        pq = self._pack_qkv()
-        po = sa._pack("out", [sa.out_proj])
-        p1 = mlp.pack1(self.mlp_norm if self.pre_norm else None)
-        p2 = mlp.pack2()
-        qkv2 = ws.qkv.view(M, 3 * inner)
-        q, k, v = ws.qkv[:, :, :inner], ws.qkv[:, :, inner:2 * inner], ws.qkv[:, :, 2 * inner:]
-        if self.pre_norm:
-            if stats_in is None:
-                stats_in = ops.row_stats(x2, self.sa_norm.eps, ws.stats)
-            ops.linear(x2, pq.w, pq.bias, qkv2, colsum=pq.colsum, rowstats=stats_in, ln_eps=self.sa_norm.eps)
-            ops.attention(q, k, v, ws.att, sa.n_heads, sa.scale)
-            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.mid, residual=x2, stats_out=ws.parts_mid)
-            mid_stats = ws.parts_mid
-            if mid_stats is None:
-                mid_stats = ops.row_stats(ws.mid, self.mlp_norm.eps, ws.stats)
-            ops.linear(ws.mid, p1.w, p1.bias, ws.hidden, colsum=p1.colsum, rowstats=mid_stats,
-                       ln_eps=self.mlp_norm.eps, gelu=True)
-            out_stats = ws.parts_out if want_stats else None
-            ops.linear(ws.hidden, p2.w, p2.bias, out2, residual=ws.mid, stats_out=out_stats)
-            return out_stats
-        else:  # post-norm (BERT): transformer.py:128-129
-            g1, b1 = norm_vectors(self.sa_norm)
-            g2, b2 = norm_vectors(self.mlp_norm)
-            ops.linear(x2, pq.w, pq.bias, qkv2)
-            ops.attention(q, k, v, ws.att, sa.n_heads, sa.scale)
-            ops.linear(ws.att.view(M, inner), po.w, po.bias, ws.tmp, residual=x2)
-            ops.layernorm(ws.tmp, g1, b1, self.sa_norm.eps, ws.mid)
-            ops.linear(ws.mid, p1.w, p1.bias, ws.hidden, gelu=True)
-            ops.linear(ws.hidden, p2.w, p2.bias, ws.tmp, residual=ws.mid)
-            ops.layernorm(ws.tmp, g2, b2, self.mlp_norm.eps, out2)
-        return None
+        super().__init__(d_model, n_heads, head_dim, False, bias, mlp_ratio, dropout, act, pre_norm, norm_eps)
 
     def forward(self, x: Tensor) -> Tensor:
-        d = self.sa_norm.normalized_shape[0]
-        x3, meta = _as_tokens(x, d)
-        out3 = torch.empty_like(x3)
-        self.run(x3, out3, self.workspace(x3.shape[0], x3.shape[1], x3.device))
-        return _restore(out3, meta)
+        return super().forward(x)
 
 
 def norm_vectors(norm: nn.LayerNorm) -> tuple[Tensor, Tensor]:
@@ -393,18 +482,134 @@ class Encoder(nn.Sequential):
 
     def run(self, x3: Tensor) -> Tensor:
         """bf16 contiguous (B, L, d) -> new tensor of the same shape; x3 is left untouched."""
-        layers = list(self)
-        if not layers or x3.numel() == 0:
-            return x3.clone()
-        B, L, _ = x3.shape
-        ws = layers[0].workspace(B, L, x3.device)
-        bufs = [torch.empty_like(x3), torch.empty_like(x3) if len(layers) > 1 else None]
-        cur, stats = x3, None
-        for i, layer in enumerate(layers):
-            stats = layer.run(cur, bufs[i % 2], ws, stats_in=stats, want_stats=i + 1 < len(layers))
-            cur = bufs[i % 2]
-        return cur
+        return _run_stack(list(self), x3, None)
 
     def forward(self, x: Tensor) -> Tensor:
         x3, meta = _as_tokens(x, self.d_model)
         return _restore(self.run(x3), meta)
+
+
+def _run_stack(layers: list, x3: Tensor, memory3: Tensor | None, final_stats: bool = False):
+    """Run a list of layers over bf16 contiguous (B, L, d) tokens with one shared workspace and two ping-pong output
+    buffers; the LayerNorm statistics travel from each layer's last GEMM to the next layer's first.
+
+    With ``final_stats`` returns ``(tokens, stats)`` where stats are the partial LayerNorm statistics of the output
+    rows (None when the stack cannot produce them) for a LayerNorm folded into whatever consumes the tokens."""
+    if not layers or x3.numel() == 0:
+        return (x3.clone(), None) if final_stats else x3.clone()
+    B, L, _ = x3.shape
+    ws = layers[0].workspace(B, L, x3.device, 0 if memory3 is None else memory3.shape[1])
+    bufs = [torch.empty_like(x3), torch.empty_like(x3) if len(layers) > 1 else None]
+    cur, stats = x3, None
+    for i, layer in enumerate(layers):
+        want = final_stats or i + 1 < len(layers)
+        stats = layer.run(cur, bufs[i % 2], ws, stats_in=stats, want_stats=want, memory3=memory3)
+        cur = bufs[i % 2]
+    return (cur, stats) if final_stats else cur
+
+
+class Decoder(nn.ModuleList):
+    """Reference ``Decoder`` (transformer.py:152-176): an ``nn.ModuleList`` of ``DecoderLayer`` called as
+    ``decoder(x, memory)``; ``forward`` additionally shares one workspace across the layers."""
+
+    def __init__(
+        self,
+        n_layers: int,
+        d_model: int,
+        n_heads: int | None = None,
+        head_dim: int | None = None,
+        cross_attn: bool = False,
+        bias: bool = True,
+        mlp_ratio: float = 4.0,
+        dropout: float = 0.0,
+        act: str = "gelu",
+        pre_norm: bool = True,
+        norm_eps: float = 1e-5,
+    ) -> None:
+        super().__init__()
+        for _ in range(n_layers):
+            self.append(
+                DecoderLayer(d_model, n_heads, head_dim, cross_attn, bias, mlp_ratio, dropout, act, pre_norm, norm_eps)
+            )
+        self.d_model = d_model
+
+    def run(self, x3: Tensor, memory3: Tensor | None = None, final_stats: bool = False):
+        """bf16 contiguous (B, L, d) [+ memory (B, Lm, d)] -> new tensor of x3's shape; inputs are left untouched.
+        ``final_stats``: also return the output rows' partial LayerNorm statistics (see `_run_stack`)."""
+        return _run_stack(list(self), x3, memory3, final_stats)
+
+    def forward(self, x: Tensor, memory: Tensor | None = None) -> Tensor:
+        x3, meta = _as_tokens(x, self.d_model)
+        m3 = None
+        if memory is not None and len(self) and self[0].ca is not None:
+            m3, _ = _as_tokens(memory, self.d_model)
+        return _restore(self.run(x3, m3), meta)
+
+
+# ----------------------------------------------------------------------------------------------- language-model ends
+def embed_tokens(ids: Tensor, token_embs: nn.Embedding, pos_embs: Tensor) -> Tensor:
+    """``token_embs(ids) + pos_embs[:L]`` (bert.py:35-36, gpt2.py:22-23, gpt.py:25-26, whisper.py:47-48):
+    (*, L) int64 -> contiguous bf16 (B, L, d) in one gather kernel."""
+    if not ids.is_cuda:
+        raise RuntimeError(
+            "pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback "
+            f"(got a {ids.device} tensor)"
+        )
+    L = ids.shape[-1]
+    if L > pos_embs.shape[0]:
+        raise ValueError(f"sequence length {L} exceeds the {pos_embs.shape[0]} rows of the position table")
+    tok = token_embs.weight.detach()
+    pos = pos_embs.detach()
+    if tok.dtype not in (torch.float32, torch.bfloat16):
+        tok = tok.float()
+    if pos.dtype != tok.dtype:
+        pos = pos.to(tok.dtype)
+    ids2 = ids.reshape(-1, L).to(torch.int64).contiguous()
+    out = torch.empty(ids2.shape[0], L, tok.shape[1], device=ids.device, dtype=torch.bfloat16)
+    return ops.embed_rows(ids2, tok.contiguous(), pos.contiguous(), out)
+
+
+class TiedLogits:
+    """``norm(x) @ token_embs.weight.T`` (gpt2.py:25-26, whisper.py:50-51) or without the norm (gpt.py:28) as one
+    GEMM: the final LayerNorm is folded into a cached bf16 copy of the embedding table (rows padded to a multiple of
+    8 so that every logits row is 16-byte aligned; the padding columns are sliced off the returned view)."""
+
+    def __init__(self) -> None:
+        self._slot = _Packed()
+
+    def _pack(self, emb: nn.Embedding, norm: nn.LayerNorm | None) -> SimpleNamespace:
+        def build() -> SimpleNamespace:
+            w32 = emb.weight.detach().float()
+            V, d = w32.shape
+            V8 = (V + 7) // 8 * 8
+            if norm is None:
+                w = torch.zeros(V8, d, device=w32.device, dtype=torch.bfloat16)
+                w[:V] = w32
+                return SimpleNamespace(w=w, bias=None, colsum=None, V=V)
+            gamma, beta = norm.weight.detach().float(), norm.bias.detach().float()
+            w = torch.zeros(V8, d, device=w32.device, dtype=torch.bfloat16)
+            w[:V] = w32 * gamma[None, :]
+            c = torch.zeros(V8, device=w32.device, dtype=torch.float32)
+            c[:V] = w32 @ beta
+            return SimpleNamespace(w=w, bias=c, colsum=w.float().sum(dim=1).contiguous(), V=V)
+
+        params = (emb.weight,) if norm is None else (emb.weight, norm.weight, norm.bias)
+        return self._slot.get(params, build)
+
+    def __call__(self, x3: Tensor, emb: nn.Embedding, norm: nn.LayerNorm | None = None,
+                 stats: Tensor | None = None) -> Tensor:
+        """x3: bf16 contiguous (B, L, d); ``stats``: partial LayerNorm statistics of its rows if the producer wrote
+        them (else one row_stats pass runs). Returns bf16 (B, L, vocab) — a view into rows of ceil8(vocab) columns."""
+        B, L, d = x3.shape
+        pk = self._pack(emb, norm)
+        V8 = pk.w.shape[0]
+        out = torch.empty(B, L, V8, device=x3.device, dtype=torch.bfloat16)
+        if B * L:
+            x2 = x3.view(B * L, d)
+            if norm is None:
+                ops.linear(x2, pk.w, None, out.view(B * L, V8))
+            else:
+                if stats is None:
+                    stats = ops.row_stats(x2, norm.eps, torch.empty(B * L, 2, device=x3.device, dtype=torch.float32))
+                ops.linear(x2, pk.w, pk.bias, out.view(B * L, V8), colsum=pk.colsum, rowstats=stats, ln_eps=norm.eps)
+        return out[:, :, :pk.V]

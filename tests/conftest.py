@@ -13,7 +13,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-FIXTURES = ["vit_cls", "vit_gap", "vit_siglip", "vit_p14", "vit_long", "whisper", "bert"]
+FIXTURES = ["vit_cls", "vit_gap", "vit_siglip", "vit_p14", "vit_long", "whisper", "bert",
+            "decoder_postnorm_cross", "decoder_causal_long", "whisper_full", "gpt2", "gpt"]
 
 
 def pytest_configure(config):
@@ -30,6 +31,7 @@ class Golden:
         self.input = z["input"]
         self.sd = {k[3:]: z[k] for k in z.files if k.startswith("sd.")}
         self.out = {k[4:]: z[k] for k in z.files if k.startswith("out.")}
+        self.extra = {k[3:]: z[k] for k in z.files if k.startswith("in.")}  # further inputs (memory, targets)
 
     def torch_sd(self):
         import torch
@@ -61,6 +63,14 @@ def build_model(g: Golden):
         m = pm.WhisperEncoder(h["n_layers"], h["d_model"], h["n_mels"])
     elif kind == "bert":
         m = pm.BERT(h["vocab_size"], h["n_layers"], h["d_model"])
+    elif kind == "decoder":
+        m = pm.Decoder(h["n_layers"], h["d_model"], cross_attn=h["cross_attn"], pre_norm=h["pre_norm"])
+    elif kind == "whisper_full":
+        m = pm.Whisper(h["vocab_size"], h["n_layers"], h["d_model"], h["n_mels"])
+    elif kind in ("gpt2", "gpt"):
+        base = pm.GPT2 if kind == "gpt2" else pm.GPT
+        # vocab_size is a class attribute, as in the reference (gpt2.py:12, gpt.py:15)
+        m = type(f"{base.__name__}Small", (base,), dict(vocab_size=h["vocab_size"]))(h["n_layers"], h["d_model"])
     else:
         raise KeyError(kind)
     m.load_state_dict(g.torch_sd(), strict=True)

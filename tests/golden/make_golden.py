@@ -22,9 +22,10 @@ import torch
 sys.path.insert(0, "/root/reference")
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 
-from pytorch_models.audio2text.whisper import WhisperEncoder  # noqa: E402
+from pytorch_models.audio2text.whisper import Whisper, WhisperEncoder  # noqa: E402
 from pytorch_models.image import ViT  # noqa: E402
-from pytorch_models.text import BERT  # noqa: E402
+from pytorch_models.text import BERT, GPT, GPT2  # noqa: E402
+from pytorch_models.transformer import Decoder  # noqa: E402
 
 from oracle.oracle_torch import randomize_  # noqa: E402
 
@@ -46,9 +47,11 @@ def vit_token_outputs(m: ViT, x: torch.Tensor) -> torch.Tensor:
     return torch.cat(outs)
 
 
-def save(name: str, model: torch.nn.Module, hyper: dict, inputs: torch.Tensor, outputs: dict, weights: bool = True):
+def save(name: str, model: torch.nn.Module, hyper: dict, inputs: torch.Tensor, outputs: dict, weights: bool = True,
+         extra: dict | None = None):
     arrays = {f"out.{k}": v.detach().numpy() for k, v in outputs.items()}
     arrays["input"] = inputs.numpy()
+    arrays.update({f"in.{k}": v.numpy() for k, v in (extra or {}).items()})
     if weights:
         arrays.update({f"sd.{k}": v.detach().numpy() for k, v in model.state_dict().items()})
     arrays["hyper"] = np.frombuffer(json.dumps(hyper).encode(), dtype=np.uint8)
@@ -88,6 +91,8 @@ def main() -> None:
     t = torch.randint(3, 1000, (2, 16))
     save("bert", b, dict(kind="bert", vocab_size=1000, n_layers=2, d_model=128), t, dict(tokens=b(t)))
 
+    decoder_cases()
+
     # C1 = BASELINE configs[0]: ViT-Ti/16 augreg 224, batch 8, random-init weights, fp32 CPU forward (reference path)
     torch.manual_seed(0)
     m = ViT.from_google("Ti/16").eval()
@@ -98,5 +103,53 @@ def main() -> None:
          torch.zeros(1), dict(pooled=per_sample(m, x), tokens=vit_token_outputs(m, x)), weights=False)
 
 
+def decoder_cases() -> None:
+    """DecoderLayer / Decoder and the models built on it (transformer.py:70-105,152-176)."""
+    def noise_(m: torch.nn.Module, seed: int) -> None:
+        randomize_(m.state_dict(), seed)
+
+    # post-norm decoder with cross-attention: not reachable through any model class, so pinned directly
+    torch.manual_seed(8)
+    dec = Decoder(2, 128, cross_attn=True, pre_norm=False).eval()
+    noise_(dec, 108)
+    x, mem = torch.randn(2, 20, 128), torch.randn(2, 37, 128)
+    save("decoder_postnorm_cross", dec, dict(kind="decoder", n_layers=2, d_model=128, cross_attn=True, pre_norm=False),
+         x, dict(tokens=dec(x, mem)), extra=dict(memory=mem))
+
+    # 300 tokens: the causal mask crosses 128-row tile and 128-column block boundaries
+    torch.manual_seed(9)
+    dec = Decoder(1, 64).eval()
+    noise_(dec, 109)
+    x = torch.randn(1, 300, 64)
+    save("decoder_causal_long", dec, dict(kind="decoder", n_layers=1, d_model=64, cross_attn=False, pre_norm=True),
+         x, dict(tokens=dec(x)))
+
+    # full Whisper (encoder + decoder with cross-attention); odd vocabulary like the real 51865 / 51866
+    torch.manual_seed(10)
+    w = Whisper(1001, 2, 128, 80).eval()
+    noise_(w, 110)
+    torch.nn.init.normal_(w.decoder.pos_embs, std=0.02)
+    torch.nn.init.normal_(w.decoder.token_embs.weight, std=0.05)
+    x, tgt = torch.randn(2, 80, 120), torch.randint(0, 1001, (2, 12))
+    save("whisper_full", w, dict(kind="whisper_full", vocab_size=1001, n_layers=2, d_model=128, n_mels=80), x,
+         dict(logits=w(x, tgt), memory=w.encoder(x)), extra=dict(targets=tgt))
+
+    # GPT-2 / GPT with a reduced vocabulary (vocab_size is a class attribute in the reference: gpt2.py:12, gpt.py:15)
+    for name, base, seed in (("gpt2", GPT2, 11), ("gpt", GPT, 12)):
+        cls = type(f"{base.__name__}Small", (base,), dict(vocab_size=777))
+        torch.manual_seed(seed)
+        m = cls(2, 64).eval()
+        noise_(m, 100 + seed)
+        torch.nn.init.normal_(m.pos_embs, std=0.02)
+        torch.nn.init.normal_(m.token_embs.weight, std=0.05)
+        t = torch.randint(0, 777, (2, 33))
+        save(name, m, dict(kind=name, vocab_size=777, n_layers=2, d_model=64), t, dict(logits=m(t)))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "decoder":  # add the decoder fixtures without rewriting the others
+        with torch.no_grad():
+            torch.set_num_threads(8)
+            decoder_cases()
+    else:
+        main()

@@ -65,6 +65,84 @@ def test_attention_matches_sdpa(L):
     _close(out, want, 0.02, 0.02)
 
 
+@pytest.mark.parametrize("L", [1, 7, 128, 129, 200, 256, 257, 448, 700, 1024])
+def test_causal_attention_matches_sdpa(L):
+    """is_causal=True of F.scaled_dot_product_attention (transformer.py:52,97): masked diagonal blocks, K/V blocks
+    above the diagonal skipped, query tiles of one item visiting different numbers of blocks."""
+    from pytorch_models_b200 import ops
+
+    B, H = 2, 2
+    g = torch.Generator(device="cuda").manual_seed(1000 + L)
+    qkv = (torch.randn(B, L, 3 * H * 64, device="cuda", generator=g) * 1.5).bfloat16()
+    out = torch.empty(B, L, H * 64, device="cuda", dtype=torch.bfloat16)
+    q, k, v = qkv[:, :, : H * 64], qkv[:, :, H * 64: 2 * H * 64], qkv[:, :, 2 * H * 64:]
+    ops.attention(q, k, v, out, H, 0.125, causal=True)
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(k), heads(v), is_causal=True).transpose(1, 2).flatten(-2)
+    _close(out, want, 0.02, 0.02)
+    # the first row attends to key 0 only: its output is v[0] exactly
+    assert torch.equal(out[:, 0], v[:, 0])
+
+
+@pytest.mark.parametrize("Lq,Lkv", [(5, 300), (300, 5), (130, 129)])
+def test_causal_attention_rectangular(Lq, Lkv):
+    """Lq != Lkv keeps SDPA's top-left alignment (key j visible to query i iff j <= i)."""
+    from pytorch_models_b200 import ops
+
+    B, H = 2, 1
+    q = torch.randn(B, Lq, 64, device="cuda").bfloat16()
+    kv = torch.randn(B, Lkv, 128, device="cuda").bfloat16()
+    out = torch.empty(B, Lq, 64, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, kv[:, :, :64], kv[:, :, 64:], out, H, 0.125, causal=True)
+    mask = torch.ones(Lq, Lkv, device="cuda", dtype=torch.bool).tril()
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(kv[:, :, :64]), heads(kv[:, :, 64:]), attn_mask=mask)
+    _close(out, want.transpose(1, 2).flatten(-2), 0.02, 0.02)
+
+
+@pytest.mark.parametrize("fold", [False, True])
+def test_linear_tanh_gelu(fold):
+    from pytorch_models_b200 import ops
+
+    M, N, K = 300, 1024, 256
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5 * 2).bfloat16()
+    b = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ref = x.float() @ w.float().T
+    if fold:
+        stats = torch.stack([torch.randn(M, device="cuda") * 0.3, torch.rand(M, device="cuda") + 0.5], 1).contiguous()
+        s = w.float().sum(1)
+        ops.linear(x, w, b, out, colsum=s, rowstats=stats, gelu="tanh")
+        ref = stats[:, 1:2] * (ref - stats[:, 0:1] * s[None]) + b
+    else:
+        ops.linear(x, w, b, out, gelu="tanh")
+        ref = ref + b
+    _close(out, F.gelu(ref, approximate="tanh"), 0.02, 0.01)
+    with pytest.raises(ValueError):
+        ops.linear(x, w, b, out, gelu="tanh", residual=out.clone())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_embed_rows(dtype):
+    from pytorch_models_b200 import ops
+
+    B, L, V, d = 3, 17, 101, 72
+    tok = torch.randn(V, d, device="cuda").to(dtype)
+    pos = torch.randn(L + 4, d, device="cuda").to(dtype)
+    ids = torch.randint(0, V, (B, L), device="cuda")
+    out = torch.empty(B, L, d, device="cuda", dtype=torch.bfloat16)
+    ops.embed_rows(ids, tok, pos, out)
+    want = (tok[ids].float() + pos[:L].float()).bfloat16()
+    assert torch.equal(out, want)
+    ids[1, 3] = V  # out of range: that row is NaN, the others are untouched
+    ops.embed_rows(ids, tok, pos, out)
+    assert bool(out[1, 3].isnan().all())
+    ok = torch.ones(B, L, dtype=torch.bool, device="cuda")
+    ok[1, 3] = False
+    assert torch.equal(out[ok], want[ok])
+
+
 def test_cross_attention_one_query():
     """The MAP-pooling shape (vit.py:41): 1 query row against L keys."""
     from pytorch_models_b200 import ops
@@ -113,8 +191,8 @@ def test_bad_arguments_raise():
         ops.attention(q, q, q, torch.empty_like(q), 3, 1.0)
 
 
-@pytest.mark.parametrize("case", ["linear:tails_tma", "linear:embed_like", "linear:fold_gelu", "attn:l197_tmem",
-                                  "attn:cross_q1", "rows:all"])
+@pytest.mark.parametrize("case", ["linear:tails_tma", "linear:embed_like", "linear:fold_gelu", "linear:fold_gelu_tanh",
+                                  "attn:l197_tmem", "attn:cross_q1", "attn:causal_l448", "attn:causal_many", "rows:all"])
 def test_native_selftest(case):
     """The stand-alone C++ harness (fp64 CPU check inside the binary) on its edge-case shapes."""
     exe = os.path.join(ROOT, "pytorch_models_b200", "b200enc_selftest")

@@ -35,6 +35,14 @@ def _run_fixture(g, m):
             ops.layernorm(tokens.view(-1, tokens.shape[-1]), gamma.contiguous(), beta.contiguous(), m.norm.eps,
                           normed.view(-1, tokens.shape[-1]))
             return dict(pooled=m(x).float().cpu().numpy(), tokens=normed.float().cpu().numpy())
+        extra = {k: torch.from_numpy(np.array(v)).cuda() for k, v in g.extra.items()}
+        if kind == "decoder":
+            return dict(tokens=m(x, extra.get("memory")).float().cpu().numpy())
+        if kind == "whisper_full":
+            return dict(logits=m(x, extra["targets"]).float().cpu().numpy(),
+                        memory=m.encoder(x).float().cpu().numpy())
+        if kind in ("gpt2", "gpt"):
+            return dict(logits=m(x).float().cpu().numpy())
         return dict(tokens=m(x).float().cpu().numpy())
 
 

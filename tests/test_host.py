@@ -81,20 +81,28 @@ def test_no_cpu_fallback():
         pm.WhisperEncoder(1, 64)(torch.randn(1, 80, 16))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pm.BERT(100, 1, 64)(torch.randint(0, 100, (1, 8)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.MHA(128).eval()(torch.randn(1, 4, 128), causal=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.MLP(128, 256, act="approximate_gelu").eval()(torch.randn(1, 4, 128))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.Decoder(1, 64, cross_attn=True)(torch.randn(1, 4, 64), torch.randn(1, 6, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.GPT2(1, 64)(torch.randint(0, 100, (1, 8)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.Whisper(100, 1, 64)(torch.randn(1, 80, 16), torch.randint(0, 100, (1, 4)))
 
 
 def test_unsupported_arguments_raise_not_implemented():
     x = torch.randn(1, 4, 128)
     mha = pm.MHA(128).eval()
     with pytest.raises(NotImplementedError):
-        mha(x, causal=True)
-    with pytest.raises(NotImplementedError):
         mha(x, attn_bias=torch.zeros(4, 4))
     with pytest.raises(NotImplementedError):
         pm.MHA(128, head_dim=32).eval()(x)
     with pytest.raises(NotImplementedError):
         pm.MHA(128, dropout=0.1).train()(x)
-    for act in ("approximate_gelu", "relu", "silu"):
+    for act in ("relu", "silu"):
         with pytest.raises(NotImplementedError):
             pm.MLP(128, 256, act=act).eval()(x)
     with pytest.raises(NotImplementedError):

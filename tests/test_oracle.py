@@ -23,6 +23,16 @@ def run_np(g: Golden) -> dict:
         )
     if h["kind"] == "whisper":
         return dict(tokens=oracle_np.whisper_encoder_forward(g.sd, g.input))
+    if h["kind"] == "decoder":
+        return dict(tokens=oracle_np.decoder(g.sd, g.input, g.extra.get("memory"), h["d_model"] // 64, h["pre_norm"],
+                                             1e-5, prefix=""))
+    if h["kind"] == "whisper_full":
+        return dict(logits=oracle_np.whisper_forward(g.sd, g.input, g.extra["targets"]),
+                    memory=oracle_np.whisper_encoder_forward(oracle_np.sub_dict(g.sd, "encoder."), g.input))
+    if h["kind"] == "gpt2":
+        return dict(logits=oracle_np.gpt2_forward(g.sd, g.input))
+    if h["kind"] == "gpt":
+        return dict(logits=oracle_np.gpt_forward(g.sd, g.input))
     return dict(tokens=oracle_np.bert_forward(g.sd, g.input))
 
 
@@ -37,6 +47,17 @@ def run_torch(g: Golden) -> dict:
         )
     if h["kind"] == "whisper":
         return dict(tokens=oracle_torch.whisper_encoder_forward(sd, x).numpy())
+    extra = {k: torch.from_numpy(np.array(v)) for k, v in g.extra.items()}
+    if h["kind"] == "decoder":
+        return dict(tokens=oracle_torch.decoder(sd, x, extra.get("memory"), h["d_model"] // 64, h["pre_norm"], 1e-5,
+                                                prefix="").numpy())
+    if h["kind"] == "whisper_full":
+        return dict(logits=oracle_torch.whisper_forward(sd, x, extra["targets"]).numpy(),
+                    memory=oracle_torch.whisper_encoder_forward(oracle_torch.sub_dict(sd, "encoder."), x).numpy())
+    if h["kind"] == "gpt2":
+        return dict(logits=oracle_torch.gpt2_forward(sd, x).numpy())
+    if h["kind"] == "gpt":
+        return dict(logits=oracle_torch.gpt_forward(sd, x).numpy())
     return dict(tokens=oracle_torch.bert_forward(sd, x).numpy())
 
 
