@@ -273,10 +273,13 @@ def main() -> None:
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
+        issued = [0]  # chunks issued so far: the two staging buffers alternate across step boundaries as well
+
         def e2e_step():
             for ci in range(n_chunks):
                 lo, hi = ci * chunk, min(B, (ci + 1) * chunk)
-                s = ci % 2
+                s = issued[0] % 2
+                issued[0] += 1
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[s])
                     stage[s][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
