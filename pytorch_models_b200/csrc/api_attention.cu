@@ -12,11 +12,11 @@ extern "C" void b200enc_debug_attention_trace(long long* buf) { g_attention_trac
 #endif
 
 namespace {
-int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
-                     cudaStream_t s) {
+int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                     const AttnParams& p, cudaStream_t s) {
   B200_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, p);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -33,13 +33,16 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
                  "b200enc_attention: leading dimension smaller than H*64");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && ldo % 8 == 0 && out_batch_stride % 8 == 0,
                  "b200enc_attention: output rows must be 16-byte aligned");
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   int rc;
   const long long qbs = B > 1 ? q_batch_stride : (long long)Lq * ldq;
   const long long kbs = B > 1 ? kv_batch_stride : (long long)Lkv * ldkv;
   if ((rc = make_tmap_bf16(&tq, q, uint64_t(H) * ATT_HD, Lq, B, ldq, qbs, ATT_HD, ATT_BQ, 128))) return rc;
   if ((rc = make_tmap_bf16(&tk, k, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, ATT_BKV, 128))) return rc;
   if ((rc = make_tmap_bf16(&tv, v, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, ATT_BKV, 128))) return rc;
+  // output: one TMA store of 32 rows x 64 columns per softmax warp; rows >= Lq of a batch are clipped by the map
+  const long long obs = B > 1 ? out_batch_stride : (long long)Lq * ldo;
+  if ((rc = make_tmap_bf16(&to, out, uint64_t(H) * ATT_HD, Lq, B, ldo, obs, ATT_HD, 32, 128))) return rc;
   AttnParams p;
   p.B = B;
   p.H = H;
@@ -58,5 +61,5 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.trace = nullptr;
 #endif
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return launch_attention(tq, tk, tv, p, s);
+  return launch_attention(tq, tk, tv, to, p, s);
 }

@@ -1,17 +1,19 @@
-// Non-causal flash-style attention for head_dim 64 on sm_100a (reference: F.scaled_dot_product_attention call at
-// pytorch_models/transformer.py:52 with attn_mask=None, dropout_p=0, is_causal=False).
+// Flash-style attention (optionally causal) for head_dim 64 on sm_100a (reference: F.scaled_dot_product_attention at
+// pytorch_models/transformer.py:52 with attn_mask=None, dropout_p=0, is_causal = MHA.forward's `causal`).
 //
 // One work item = (batch, head, pair of 128-row query tiles). One persistent CTA per SM loops over items; key/value
 // rows stream through a 3-stage TMA ring in blocks of 128 with an online softmax. The two query tiles ping-pong so
-// the tensor core works on one tile while the other tile's softmax runs:
+// the tensor core works on one tile while the other tile's softmax runs. 384 threads:
 //   warp 0      : TMA producer (Q pair, double-buffered across items; K/V blocks)
-//   warp 1      : tcgen05.mma issuer, order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
+//   warp 1      : tcgen05.mma issuer, one stream across items in the order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
 //                   S_t = Q_t K_j^T          -> TMEM, fp32, 128 columns per tile
-//                   O_t[j&1] = P_t V_j       -> TMEM, 64 columns, double-buffered; P_t read from TMEM as the A operand
-//   warps 2..5  : softmax warpgroup of tile 0, warps 6..9 : tile 1. One thread per query row (= TMEM lane):
-//                 two passes of tcgen05.ld over S (row max, then exp2 with the softmax scale folded in), P written
-//                 back over S as packed bf16, running (max, sum) and the fp32 output accumulator in registers;
-//                 the rescale of the accumulator is merged into the FMA that adds the next P.V block.
+//                   O_t (+)= P_t V_j         -> TMEM, 64 columns, accumulated in place; P_t is the TMEM A operand
+//   warps 2..3  : idle (they only complete warpgroup 0 so that it can hand registers to the softmax warpgroups)
+//   warps 4..7  : softmax warpgroup of tile 0, warps 8..11 : tile 1. One thread per query row (= TMEM lane): the
+//                 whole 128-column S row is read ONCE into registers (setmaxnreg gives these warps 208 registers),
+//                 row max, exp2 with the softmax scale folded in, P written back over S as packed bf16.
+//                 The maximum is updated lazily (only when a row outgrows 2^8 of head-room), so the accumulator
+//                 in TMEM is rescaled rarely; the normalised output leaves through one TMA store per warp.
 // Q/K/V are read straight out of the fused QKV activation [rows, 3d] through strided 3-D tensor maps (no head
 // transpose is materialised); the output is written head-interleaved as [rows, d] for out_proj.
 #pragma once
@@ -22,13 +24,18 @@ namespace b200 {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;  // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1, 2: softmax
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
 constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
 constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
-constexpr int ATT_SMEM_BAR = ATT_SMEM_V + ATT_KV_STAGES * ATT_TILE_BYTES;
+constexpr int ATT_STG_BYTES = 32 * 128;                          // one softmax warp's output rows: 32 x 64 bf16
+constexpr int ATT_SMEM_STG = ATT_SMEM_V + ATT_KV_STAGES * ATT_TILE_BYTES;  // 8 warps, 1024-aligned
+constexpr int ATT_SMEM_BAR = ATT_SMEM_STG + 8 * ATT_STG_BYTES;
+constexpr int ATT_SOFTMAX_REGS = 208;  // setmaxnreg: the increase blocks until the control warpgroup has released enough
+constexpr int ATT_CONTROL_REGS = 88;   //   (the kernel starts with 168 x 384 = 64512 registers: 4 x 32 x 88 + 8 x 32 x 208 uses exactly that)
+constexpr float ATT_RESCALE_LOG2 = 8.0f;  // head-room of the lazily updated softmax maximum: P <= 2^8
 constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 256;
 
 struct AttnParams {
@@ -57,9 +64,72 @@ struct AttnParams {
 #define ATT_EV(ev) do {} while (0)
 #endif
 
+// One 128-column block of the online softmax for one query row (= one thread = one TMEM lane).
+// The whole S row is pulled into registers with back-to-back tcgen05.ld (one wait), so S is read once; P goes back
+// over the same TMEM columns as packed bf16 for the TS MMA. n_chunks (warp-uniform) = 32-column chunks that hold
+// valid columns; `masked` (warp-uniform): the block has a partial last chunk or holds the causal diagonal — columns
+// >= lim are set to -inf before the maximum, after which the exponential pass needs no predicates.
+// (One copy of this code on purpose: two inlined specialisations made ptxas spill the 128-register row.)
+__device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool masked, int lim, float c, float& m,
+                                              float& l, float& alpha, bool& rescale) {
+  uint32_t v[4][32];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+    if (ch < n_chunks) tmem_ld32(tS + ch * 32, v[ch]);
+  tmem_wait_ld();
+  if (masked) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (ch * 32 + i >= lim) v[ch][i] = 0xff800000u;
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (ch < n_chunks) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[ch][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[ch][i + 1]));
+      }
+    }
+  }
+  const float m_new = fmaxf(m, fmaxf(mx0, mx1));
+  // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
+  // the first block, where m = -inf)
+  rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
+  if (rescale) {
+    alpha = fast_exp2((m - m_new) * c);
+    m = m_new;
+    l *= alpha;
+  }
+  const float2 c2 = make_float2(c, c);
+  const float2 nmc2 = make_float2(-m * c, -m * c);
+  float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (ch < n_chunks) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 e = __ffma2_rn(make_float2(__uint_as_float(v[ch][2 * i]), __uint_as_float(v[ch][2 * i + 1])), c2,
+                                    nmc2);
+        const float2 pr = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+        if (i & 1) sum1 = __fadd2_rn(sum1, pr); else sum0 = __fadd2_rn(sum0, pr);
+        pk[i] = pack_bf16x2(pr.x, pr.y);
+      }
+      tmem_st16(tS + ch * 16, pk);
+    }
+  }
+  const float2 sum = __fadd2_rn(sum0, sum1);
+  l += sum.x + sum.y;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                 const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + ATT_SMEM_BAR;
@@ -73,7 +143,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int lane = threadIdx.x & 31;
 #ifdef ATT_TRACE
   int tr_n = 0;
-  const int tr_role = warp == 0 ? 0 : warp == 1 ? 1 : warp < 6 ? 2 : 3;
+  const int tr_role = warp == 0 ? 0 : warp == 1 ? 1 : warp < 8 ? 2 : 3;
 #endif
 
   if (threadIdx.x == 0) {
@@ -96,6 +166,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {
     tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -105,7 +176,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O buffers at t*256 + 128 and t*256 + 192
+  // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O accumulator at t*256 + [128,192)
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
   // K/V blocks a query tile has to visit: all of them, or with a causal mask only those up to its last row's diagonal
   auto tile_blocks = [&](int item, int t) {
@@ -116,6 +187,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   };
   auto item_blocks = [&](int item) { return max(tile_blocks(item, 0), tile_blocks(item, 1)); };
 
+  if (warp < 4) setmaxnreg_dec<ATT_CONTROL_REGS>();  // whole warpgroup 0 (the two idle warps included)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
     uint32_t it = 0, stage = 0, phase = 0;
@@ -190,12 +262,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes (+128 in the descriptor); P: 8 TMEM columns
         const uint64_t dv0 = make_smem_desc_sw128(sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES, 16, 1024);
         const uint32_t pa0 = tmem_base + t * 256;
-        const uint32_t d_o = tmem_base + t * 256 + 128 + (g[t] & 1u) * 64;
+        const uint32_t d_o = tmem_base + t * 256 + 128;
+        const uint32_t acc0 = bl.j > 0 ? 1u : 0u;  // the first block of a tile overwrites O, later ones accumulate
         const int ksteps = n_mma_of(bl.j) / 16;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_BKV / 16; ++k)
-            if (k < ksteps) umma_ts(d_o, pa0 + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : 0u);
+            if (k < ksteps) umma_ts(d_o, pa0 + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : acc0);
           umma_commit(bar(O_FULL + t));
         }
         __syncwarp();
@@ -250,15 +323,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / output warpgroups
-    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    setmaxnreg_inc<ATT_SOFTMAX_REGS>();  // a whole S row (128 fp32) lives in registers
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
     const int qd = warp & 3;        // TMEM lane quarter
     const int r = qd * 32 + lane;   // row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
     const uint32_t tS = tmem_base + t * 256 + lane_off;
     const uint32_t tO = tS + 128;
     const float c = p.scale_log2e;
+    const uint32_t stg = sbase + ATT_SMEM_STG + uint32_t(warp - 4) * ATT_STG_BYTES;  // this warp's 32 x 128 B staging
     uint32_t g = 0;  // blocks processed so far by this tile
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qp = item % p.n_qp;
@@ -270,115 +345,94 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (nb == 0) continue;                              // tile not scheduled at all (same rule as the MMA warp)
       const bool warp_live = row0 + qd * 32 < p.Lq;       // any valid row in this warp?
       const int qrow = row0 + r;
-      float m = -INFINITY, l = 0.0f, alpha_prev = 0.0f;
-      float o[ATT_HD];
-#pragma unroll
-      for (int i = 0; i < ATT_HD; ++i) o[i] = 0.0f;
-
-      auto accumulate_o = [&](uint32_t gprev) {
-        // o = o * alpha(block) + P.V(block), reading the O buffer that block used (its O_FULL was already awaited)
-        if (warp_live) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tO + (gprev & 1u) * 64, v0);
-          tmem_ld32(tO + (gprev & 1u) * 64 + 32, v1);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o[i] = fmaf(o[i], alpha_prev, __uint_as_float(v0[i]));
-            o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(v1[i]));
-          }
-        }
-      };
+      // m: the maximum the exponentials are taken against. It trails the true running maximum by at most
+      // ATT_RESCALE_LOG2 (in the log2 domain), so P <= 2^ATT_RESCALE_LOG2 and the accumulator in TMEM is rescaled
+      // only when some row of the warp outgrows that head-room (rare after the first block).
+      float m = -INFINITY, l = 0.0f;
 
       for (int j = 0; j < nb; ++j, ++g) {
         const int nvalid = min(ATT_BKV, p.Lkv - j * ATT_BKV);
-        const int nchunks = (nvalid + 31) >> 5;
         // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
         const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
         const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
         mbar_wait(bar(S_FULL + t), g & 1u);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
-        float alpha = 0.0f;
+        float alpha = 1.0f;
+        bool rescale = false;
         if (warp_live) {
-          // pass 1: row maximum over the valid columns
-          float mx = -INFINITY;
-          for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(tS + ch * 32, v);
-            tmem_wait_ld();
-            if (!diag && ch * 32 + 32 <= nvalid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < lim) ? __uint_as_float(v[i]) : -INFINITY);
-            }
-          }
-          const float m_new = fmaxf(m, mx);
-          alpha = fast_exp2((m - m_new) * c);
-          const float mc = m_new * c;
-          float lsum = 0.0f;
-          // pass 2: p = exp2(s*c - m*c), row sum, P -> packed bf16 over the S columns
-          for (int ch = 0; ch < nchunks; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(tS + ch * 32, v);
-            tmem_wait_ld();
-            uint32_t pk[16];
-            const bool full = !diag && ch * 32 + 32 <= nvalid;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-              float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-              if (!full) {
-                p0 = (ch * 32 + 2 * i < lim) ? p0 : 0.0f;
-                p1 = (ch * 32 + 2 * i + 1 < lim) ? p1 : 0.0f;
-              }
-              lsum += p0 + p1;
-              pk[i] = pack_bf16x2(p0, p1);
-            }
-            tmem_st16(tS + ch * 16, pk);
-          }
-          tmem_wait_st();
-          l = l * alpha + lsum;
-          m = m_new;
+          const bool masked = diag || (nvalid & 31) != 0;
+          softmax_block(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
         }
-        // O_FULL of the previous block must be observed BEFORE this block's P is published: once P_FULL(j) is
-        // complete the tensor core may finish P.V(j) and flip O_FULL again, and a parity wait that is lapped by two
-        // phase completions never returns. (The data of block j-1 is still safe afterwards: O is double-buffered.)
         if (j > 0) {
+          // P.V(j-1) must have landed before O is rescaled or overwritten by P.V(j). Waiting here, before the
+          // arrive below, also keeps the parity wait safe: once this warp publishes P(j) the tensor core may finish
+          // P.V(j) and flip O_FULL again, and a parity wait that is lapped by two flips would never return.
           mbar_wait(bar(O_FULL + t), (g - 1) & 1u);
           tc_fence_after();
+          if (rescale) {  // warp-uniform
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tO, o0);
+            tmem_ld32(tO + 32, o1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            }
+            tmem_st32(tO, o0);
+            tmem_st32(tO + 32, o1);
+          }
         }
+        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
         if (lane == 0 && qd == 2) ATT_EV(210 + t);
-        // fold in the previous block's P.V while the tensor core works on this one
-        if (j > 0) accumulate_o(g - 1);
-        alpha_prev = alpha;
       }
       mbar_wait(bar(O_FULL + t), (g - 1) & 1u);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
       tc_fence_after();
-      accumulate_o(g - 1);
       if (lane == 0 && qd == 2) ATT_EV(220 + t);
-      tc_fence_before();
-      // normalise and write the 64 output columns of this head
-      if (qrow < p.Lq) {
+      // normalise the 64 output columns of this head and hand the warp's 32 rows to one TMA store (rows >= Lq are
+      // clipped by the tensor map)
+      if (warp_live) {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tO, o0);
+        tmem_ld32(tO + 32, o1);
+        if (elect_one()) tma_store_wait_read<0>();  // the previous item's store has finished reading the staging
+        __syncwarp();
+        tmem_wait_ld();
         const float inv = 1.0f / l;
-        __nv_bfloat16* orow = p.out + (long long)b * p.out_batch_stride + (long long)qrow * p.ldo + h * ATT_HD;
+        uint8_t* dst = smem + ATT_SMEM_STG + (warp - 4) * ATT_STG_BYTES + lane * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 w;
-          w.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-          w.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-          w.z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-          w.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-          *(reinterpret_cast<uint4*>(orow) + i) = w;
+          if (i < 4) {
+            w.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+          } else {
+            w.x = pack_bf16x2(__uint_as_float(o1[8 * i - 32]) * inv, __uint_as_float(o1[8 * i - 31]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o1[8 * i - 30]) * inv, __uint_as_float(o1[8 * i - 29]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o1[8 * i - 28]) * inv, __uint_as_float(o1[8 * i - 27]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o1[8 * i - 26]) * inv, __uint_as_float(o1[8 * i - 25]) * inv);
+          }
+          *reinterpret_cast<uint4*>(dst + ((i ^ (lane & 7)) << 4)) = w;  // 128B swizzle of the store's tensor map
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {  // bulk groups are per thread: elect.sync picks the same lane of a full warp every time
+          tma_store_3d(&tmO, stg, h * ATT_HD, row0 + qd * 32, b);
+          tma_store_commit();
+        }
+        __syncwarp();
       }
+      tc_fence_before();  // the TMEM reads above are ordered before this warp's next P_FULL arrive
       if (lane == 0 && qd == 2) ATT_EV(230 + t);
     }
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -12,7 +12,7 @@ if [ ${#cases[@]} -eq 0 ]; then mapfile -t cases < <($BIN list); fi
 fail=0
 for c in "${cases[@]}"; do
   echo "=== $c" >> "$LOG"
-  timeout 120 $BIN "$c" >> "$LOG" 2>&1
+  timeout ${CASE_TIMEOUT:-120} $BIN "$c" >> "$LOG" 2>&1
   rc=$?
   echo "=== $c rc=$rc" >> "$LOG"
   if [ $rc -ne 0 ]; then fail=$((fail+1)); fi
