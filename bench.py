@@ -191,7 +191,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
-    ap.add_argument("--chunk", type=int, default=256, help="images per H2D/compute pipeline chunk in the e2e leg")
+    ap.add_argument("--chunk", type=int, default=0,
+                    help="images per H2D/compute pipeline chunk in the e2e leg (0 = the whole per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -264,7 +265,7 @@ def main() -> None:
     # ---- end to end: pinned host images -> H2D -> forward -> D2H embeddings, chunks pipelined over two streams
     e2e = None
     if not args.no_e2e:
-        chunk = min(args.chunk, B)
+        chunk = min(args.chunk, B) if args.chunk > 0 else B
         n_chunks = (B + chunk - 1) // chunk
         copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         out_dim = y.shape[1:]
@@ -309,7 +310,8 @@ def main() -> None:
         e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "img/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
                "d2h_bytes_per_step": out_host.numel() * out_host.element_size(),
-               "pipeline": f"{n_chunks} chunks of {chunk} images, copy/compute on two streams"}
+               "pipeline": f"{n_chunks} chunk(s) of {chunk} images per step on two staging buffers: the H2D copy of a chunk "
+                           "overlaps the forward of the previous one (also across step boundaries)"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM), per-launch CUDA events on the launching stream
     roofline = None

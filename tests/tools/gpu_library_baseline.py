@@ -9,7 +9,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import pytorch_models_b200 as pm  # noqa: E402
 from bench import CONFIGS, synthetic_weights_  # noqa: E402
