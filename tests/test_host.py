@@ -169,3 +169,47 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_tied_logits_pack_folds_final_norm_and_pads_vocabulary():
+    """TiedLogits: norm(x) @ E^T as rstd*(x W'^T - mean*s) + c with the table padded to a multiple of 8 rows
+    (gpt2.py:25-26, whisper.py:50-51); the cache follows in-place edits of the embedding table."""
+    from pytorch_models_b200.transformer import TiedLogits
+
+    torch.manual_seed(0)
+    V, d = 101, 64
+    emb, norm = torch.nn.Embedding(V, d), torch.nn.LayerNorm(d)
+    torch.nn.init.normal_(norm.weight, 1.0, 0.2)
+    torch.nn.init.normal_(norm.bias, 0.0, 0.2)
+    tl = TiedLogits()
+    pk = tl._pack(emb, norm)
+    assert pk.w.shape == (104, d) and pk.V == V and pk.w.dtype == torch.bfloat16
+    assert not pk.w[V:].any() and not pk.bias[V:].any() and not pk.colsum[V:].any()
+    x = torch.randn(7, d) * 1.5 + 0.3
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + norm.eps).rsqrt()
+    got = rstd * (x @ pk.w.float().T - mean * pk.colsum[None]) + pk.bias
+    want = norm(x) @ emb.weight.T
+    torch.testing.assert_close(got[:, :V], want, atol=5e-2, rtol=2e-2)  # bf16-rounded table
+    assert tl._pack(emb, norm) is pk
+    with torch.no_grad():
+        emb.weight.mul_(2.0)
+    assert tl._pack(emb, norm) is not pk
+    plain = TiedLogits()._pack(emb, None)
+    assert plain.bias is None and plain.colsum is None and plain.w.shape == (104, d)
+
+
+def test_decoder_modules_mirror_reference_structure():
+    """DecoderLayer / Decoder keep the reference's attribute names, child order and call signatures
+    (transformer.py:70-105,152-176); EncoderLayer derives from DecoderLayer as in the reference (:108)."""
+    layer = pm.DecoderLayer(128, cross_attn=True)
+    assert [n for n, _ in layer.named_children()] == ["sa_norm", "sa", "ca_norm", "ca", "mlp_norm", "mlp"]
+    assert pm.DecoderLayer(128).ca is None and pm.DecoderLayer(128).ca_norm is None
+    assert issubclass(pm.EncoderLayer, pm.DecoderLayer)
+    dec = pm.Decoder(3, 128, cross_attn=True, pre_norm=False)
+    assert isinstance(dec, torch.nn.ModuleList) and len(dec) == 3 and not dec[0].pre_norm
+    assert len(dec.state_dict()) == 3 * (2 * 3 + 8 * 2 + 4)
+    assert pm.GPT2.vocab_size == 50257 and pm.GPT2.max_seq_len == 1024 and pm.GPT.vocab_size == 40478
+    assert pm.WhisperDecoder.max_seq_len == 448
+    m = pm.Whisper.from_openai("tiny")
+    assert m.decoder.token_embs.weight.shape == (51865, 384) and len(m.decoder.layers) == 4

@@ -179,3 +179,62 @@ def test_openai_whisper_encoder_loader_matches_reference():
     ours = pm.WhisperEncoder(2, 128, 80)
     ours.load_openai_state_dict(sd)
     _same(ref.encoder, ours)
+    # the full model (encoder + decoder with cross-attention)
+    full = pm.Whisper(300, 2, 128, 80)
+    full.load_openai_state_dict(sd)
+    _same(ref, full)
+
+
+def test_hf_gpt2_loader_matches_reference():
+    _ref()
+    from pytorch_models.text import GPT2 as RGPT2
+
+    g = torch.Generator().manual_seed(4)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    d, n_layers, vocab = 64, 2, 211
+    sd = {"transformer.wte.weight": r(vocab, d), "transformer.wpe.weight": r(1024, d),
+          "transformer.ln_f.weight": r(d), "transformer.ln_f.bias": r(d)}
+    for i in range(n_layers):
+        b = f"transformer.h.{i}"
+        sd.update({f"{b}.ln_1.weight": r(d), f"{b}.ln_1.bias": r(d), f"{b}.ln_2.weight": r(d), f"{b}.ln_2.bias": r(d),
+                   f"{b}.attn.c_attn.weight": r(d, 3 * d), f"{b}.attn.c_attn.bias": r(3 * d),
+                   f"{b}.attn.c_proj.weight": r(d, d), f"{b}.attn.c_proj.bias": r(d),
+                   f"{b}.mlp.c_fc.weight": r(d, 4 * d), f"{b}.mlp.c_fc.bias": r(4 * d),
+                   f"{b}.mlp.c_proj.weight": r(4 * d, d), f"{b}.mlp.c_proj.bias": r(d)})
+    small = dict(vocab_size=vocab)
+    torch.manual_seed(0)
+    ref = type("RS", (RGPT2,), small)(n_layers, d)
+    torch.manual_seed(0)
+    ours = type("OS", (pm.GPT2,), small)(n_layers, d)
+    ref.load_hf_state_dict(dict(sd))
+    ours.load_hf_state_dict(dict(sd))
+    _same(ref, ours)
+
+
+def test_openai_gpt_array_loader_matches_reference():
+    """The reference inlines this conversion in GPT.from_openai (gpt.py:52-91, behind a download); restated here on
+    the same flat parameter list."""
+    _ref()
+    rng = np.random.default_rng(5)
+    d, n_layers, vocab, ctx = 64, 2, 97, 512
+    r = lambda *s: rng.standard_normal(s).astype(np.float32)  # noqa: E731
+    params = [r(ctx, d), r(vocab, d)]
+    for _ in range(n_layers):
+        params += [r(1, d, 3 * d), r(3 * d), r(1, d, d), r(d), r(d), r(d), r(1, d, 4 * d), r(4 * d), r(1, 4 * d, d),
+                   r(d), r(d), r(d)]
+    ours = type("OS", (pm.GPT,), dict(vocab_size=vocab))(n_layers, d)
+    ours.load_openai_arrays(params)
+    t = [torch.from_numpy(p) for p in params]
+    sd = ours.state_dict()
+    assert torch.equal(sd["pos_embs"], t[0]) and torch.equal(sd["token_embs.weight"], t[1])
+    for i in range(n_layers):
+        o = 2 + 12 * i
+        wq, wk, wv = t[o].squeeze(0).chunk(3, -1)
+        assert torch.equal(sd[f"layers.{i}.sa.q_proj.weight"], wq.T)
+        assert torch.equal(sd[f"layers.{i}.sa.k_proj.weight"], wk.T)
+        assert torch.equal(sd[f"layers.{i}.sa.v_proj.bias"], t[o + 1].chunk(3, -1)[2])
+        assert torch.equal(sd[f"layers.{i}.sa.out_proj.weight"], t[o + 2].squeeze(0).T)
+        assert torch.equal(sd[f"layers.{i}.sa_norm.weight"], t[o + 4])
+        assert torch.equal(sd[f"layers.{i}.mlp.linear1.weight"], t[o + 6].squeeze(0).T)
+        assert torch.equal(sd[f"layers.{i}.mlp.linear2.bias"], t[o + 9])
+        assert torch.equal(sd[f"layers.{i}.mlp_norm.bias"], t[o + 11])
