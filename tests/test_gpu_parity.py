@@ -187,3 +187,37 @@ def test_cuda_graph_replay_is_bit_identical(golden):
         assert torch.equal(y1, eager) and torch.equal(y2, m(x2))
     with pytest.raises(ValueError):
         graphed(x[:1])
+
+
+def test_decoder_generator_greedy_matches_oracle(golden):
+    """DecoderGenerator (generator.py:16-39) on the GPT-2 fixture: greedy continuation of a prompt, token by token,
+    against the fp32 oracle fed the same growing prefix. 1-D token input, as the reference's generator passes it."""
+    from pytorch_models_b200.text import DecoderGenerator
+
+    class Tok:  # stand-in tokenizer: "3 5 8" <-> [3, 5, 8]
+        eos_token_id = -1
+
+        def encode(self, s):
+            return [int(t) for t in s.split()]
+
+        def decode(self, ids):
+            return " ".join(str(i) for i in ids)
+
+    g = golden("gpt2")
+    m = build_model(g).cuda()
+    out = DecoderGenerator(m, Tok()).generate("5 17 300 2 41", max_tokens=6)
+    got = [int(t) for t in out.split()]
+    assert len(got) == 11 and got[:5] == [5, 17, 300, 2, 41]
+    sd = g.torch_sd()
+    want = got[:5]
+    with torch.no_grad():
+        for step in range(6):
+            logits = oracle_torch.gpt2_forward(sd, torch.tensor(want))[-1]
+            top2 = logits.topk(2).values
+            nxt = int(logits.argmax())
+            if nxt != got[5 + step]:
+                # a bf16 near-tie may legitimately flip the argmax: accept only if the oracle's margin is tiny
+                assert float(top2[0] - top2[1]) < 0.05 * float(logits.std()), (step, nxt, got[5 + step])
+                nxt = got[5 + step]
+            want.append(nxt)
+    assert want == got
