@@ -364,13 +364,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const bool masked = diag || (nvalid & 31) != 0;
           softmax_block(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
         }
-        if (j > 0) {
-          // P.V(j-1) must have landed before O is rescaled or overwritten by P.V(j). Waiting here, before the
-          // arrive below, also keeps the parity wait safe: once this warp publishes P(j) the tensor core may finish
-          // P.V(j) and flip O_FULL again, and a parity wait that is lapped by two flips would never return.
+        if (j > 0 && rescale) {  // warp-uniform
+          // P.V(j-1) must have landed before O is rescaled. The parity wait is safe although most blocks skip it:
+          // O_FULL has completed either g-1 or g phases at this point (P.V(j) cannot even be issued before this
+          // warp publishes P(j) below), and the two cases differ in parity. When there is nothing to rescale the
+          // wait is not needed at all: the tensor core accumulates P.V(j) onto O in issue order.
           mbar_wait(bar(O_FULL + t), (g - 1) & 1u);
           tc_fence_after();
-          if (rescale) {  // warp-uniform
+          {
             uint32_t o0[32], o1[32];
             tmem_ld32(tO, o0);
             tmem_ld32(tO + 32, o1);

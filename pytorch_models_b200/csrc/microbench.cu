@@ -153,6 +153,50 @@ void run_mix(const char* name, int sms, float* out, long long* cyc) {
   }
 }
 
+// TMEM read / write throughput: every warp of the CTA streams its 32-lane quarter with tcgen05.ld / tcgen05.st x32.
+#include "ptx.cuh"
+template <bool kStore>
+__global__ void tmem_kernel(float* out, long long* cycles, int iters) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    b200::tmem_alloc<512>(b200::smem_u32(&slot));
+    b200::tmem_relinquish();
+  }
+  b200::tc_fence_before();
+  __syncthreads();
+  b200::tc_fence_after();
+  const uint32_t base = slot + (uint32_t((warp & 3) * 32) << 16);
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = threadIdx.x + i;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t col = ((warp >> 2) * 128 + c * 32) & 511;
+      if (kStore) {
+        b200::tmem_st32(base + col, v);
+      } else {
+        b200::tmem_ld32(base + col, v);
+      }
+    }
+    if (kStore) b200::tmem_wait_st(); else b200::tmem_wait_ld();
+    acc += v[it & 31];
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float(acc);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  b200::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    b200::tc_fence_after();
+    b200::tmem_dealloc<512>(slot);
+  }
+}
+
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -193,6 +237,21 @@ int main() {
       printf("%-36s %4d threads/SM: %8lld clk -> %.2f exp per clk per SM\n",
              mode == 3 ? "softmax row slice, compiler schedule" : "softmax row slice, batched EX2", threads, mx,
              double(threads) * it2 * 64 / double(mx));
+    }
+  }
+  for (int store = 0; store < 2; ++store) {
+    for (int threads : {128, 256, 512}) {
+      const int it3 = 2048;
+      for (int rep = 0; rep < 2; ++rep) {
+        if (store) tmem_kernel<true><<<sms, threads>>>(out, cyc, it3); else tmem_kernel<false><<<sms, threads>>>(out, cyc, it3);
+        cudaDeviceSynchronize();
+      }
+      long long h[256];
+      cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("TMEM %s x32, %3d threads/SM: %.1f bytes per clk per SM\n", store ? "st" : "ld", threads,
+             double(threads) * it3 * 4 * 32 * 4 / double(mx));
     }
   }
   run_mix<0>("EX2 + LOP", sms, out, cyc);
