@@ -353,6 +353,8 @@ def main() -> None:
             # algorithmic bytes for the same four launches average 1.39e9
             "traffic": 1.39e9 if (args.config == "c2" and B == 1024) else None,
             "traffic_source": "ncu --set full, profiles/r01/ncu_full_layer_summary.md (QKV 1.20, out_proj 0.91, FC1 1.51, FC2 1.93 GB)",
+            "timing": "CUDA events around every launch of one extra forward on the launching stream, right after the "
+                      "timed region (same process, same buffers, clocks already settled)",
             "launches_per_step": by_kernel["b200enc_linear"][1], "avg_launch_ms": gemm_ms / by_kernel["b200enc_linear"][1],
             "share_of_step": gemm_ms / total_ms,
             "by_shape": {k: {"launches": v[2], "avg_ms": round(v[0] / v[2], 4), "tflops": round(v[1] / v[0] * 1e-9, 1)}
