@@ -303,6 +303,8 @@ static const LinearCase kLinearCases[] = {
     {"perf_qkv_direct", 1, 25216, 2304, 768, true, false, false, false, true, false, 0, 16, 20},
     {"perf_qkv_l2fit", 1, 8192, 2304, 768, true, false, false, false, false, false, 0, 16, 60},
     {"perf_qkv_big", 1, 201728, 2304, 768, true, false, false, false, false, false, 0, 8, 10},
+    {"perf_out_big", 1, 201728, 768, 768, false, false, true, false, false, false, 0, 8, 10},
+    {"perf_fc2_big", 1, 201728, 768, 3072, false, false, true, false, false, false, 0, 8, 10},
     {"perf_fc1_big", 1, 201728, 3072, 768, true, true, false, false, false, false, 0, 8, 10},
     {"perf_k4096", 1, 25216, 2304, 4096, false, false, false, false, false, false, 0, 8, 10},
 };
