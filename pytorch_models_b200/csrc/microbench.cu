@@ -263,6 +263,15 @@ int main() {
   run_mix<7>("FFMA2 + EX2 + FADD2 + F2FP", sms, out, cyc);
   run_mix<11>("FFMA2 + EX2 + FADD2 + PRMT", sms, out, cyc);
   run_mix<25>("FFMA2 + EX2 + 2 FADD + PRMT", sms, out, cyc);
+  {
+    int o_plain = 0, o_tmem = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o_plain, pipe_kernel<0>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o_tmem, tmem_kernel<false>, 256, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, tmem_kernel<false>);
+    printf("occupancy (CTAs of 256 threads per SM): plain kernel %d, kernel that uses tcgen05.alloc %d (regs %d)\n", o_plain,
+           o_tmem, fa.numRegs);
+  }
   printf("cuda status: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
