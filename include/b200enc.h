@@ -138,6 +138,17 @@ int b200enc_embed_rows(const long long* ids, long long rows, int L, const void* 
  */
 int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, void* rows, void* stream);
 
+/*
+ * Whisper audio front end: out[n][m][t] = (max(log10(mel[n][m][t]), max_n - 8) + 4) / 4 with
+ * mel = filters @ |STFT(audio, n_fft 400, hop 160, periodic Hann, centred, reflect padded)|^2, t < T = L / 160 and
+ * max_n the maximum of the log-mel values of sample n. Replaces WhisperPreprocessor.forward
+ * (audio2text/whisper.py:143-148) = MelSpectrogram / Spectrogram (audio/spectrogram.py:15-16,44-45). fp32 throughout.
+ * audio [N][audio_stride] (L valid samples each, L > 200); filters_t [201][n_mels] = the mel filter bank transposed;
+ * out [N][n_mels][T] contiguous; sample_max: N ints of scratch.
+ */
+int b200enc_whisper_logmel(const float* audio, long long audio_stride, int N, int L, const float* filters_t, int n_mels,
+                           float* out, int* sample_max, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,3 +236,21 @@ def gpt_forward(sd: dict, tokens: np.ndarray, eps: float = 1e-5) -> np.ndarray:
     x = lm_embed(sd, tokens)
     x = decoder(sd, x, None, x.shape[-1] // 64, False, eps, "approximate_gelu")
     return (x @ sd["token_embs.weight"].T).astype(F32)
+
+
+def whisper_logmel(audio: np.ndarray, filters: np.ndarray) -> np.ndarray:
+    """WhisperPreprocessor.forward (whisper.py:143-148): torch.stft(x, 400, 160, hann, center=True, reflect)
+    (audio/spectrogram.py:15-16) restated as explicit framing + rfft in float64, mel projection (:44-45), drop of the
+    last frame, log10, per-sample floor at max - 8 and the (x + 4) / 4 rescale."""
+    n_fft, hop = 400, 160
+    x = np.asarray(audio, dtype=np.float64)
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(n_fft // 2, n_fft // 2)], mode="reflect")
+    n_frames = 1 + x.shape[-1] // hop
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    window = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n_fft) / n_fft)  # torch.hann_window(400): periodic
+    power = np.abs(np.fft.rfft(xp[..., idx] * window, axis=-1)) ** 2       # (..., frames, 201)
+    mel = np.swapaxes(power @ np.asarray(filters, dtype=np.float64).T, -1, -2)[..., :-1]
+    with np.errstate(divide="ignore"):
+        logmel = np.log10(np.maximum(mel, 0.0))
+    floor = logmel.reshape(*logmel.shape[:-2], -1).max(-1)[..., None, None] - 8.0
+    return ((np.maximum(logmel, floor) + 4.0) / 4.0).astype(F32)

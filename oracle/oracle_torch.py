@@ -167,6 +167,16 @@ def gpt_forward(sd: dict, tokens: Tensor, eps: float = 1e-5) -> Tensor:
     return x @ sd["token_embs.weight"].T
 
 
+def whisper_logmel(audio: Tensor, filters: Tensor) -> Tensor:
+    """WhisperPreprocessor.forward (whisper.py:143-148) on top of MelSpectrogram / Spectrogram
+    (audio/spectrogram.py:15-16,44-45); ``filters`` is the module's (n_mels, 201) buffer."""
+    spec = torch.stft(audio, 400, 160, window=torch.hann_window(400), return_complex=True).abs().square()
+    x = (filters @ spec)[..., :-1]
+    x = x.clamp(0).log10()
+    x = x.maximum(x.flatten(-2).max(-1, keepdim=True)[0].unsqueeze(-1) - 8)
+    return (x + 4) / 4
+
+
 def randomize_(sd: dict, seed: int) -> dict:
     """Seeded noise into the tensors the reference zero/one-initialises (cls_token, pe, pos_embs, probe, LayerNorm
     affine: vit.py:65-66, whisper.py:24), so those code paths are exercised (SURVEY §8(d) recipe)."""

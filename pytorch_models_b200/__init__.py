@@ -2,10 +2,10 @@
 gau-nernst/pytorch-models — ``transformer.py`` (LayerNorm, MHA, MLP) plus the ViT patch embedding — behind the
 reference's module API. Kernels live in ``csrc/`` and are reached through the C-ABI in ``include/b200enc.h``."""
 from . import _lib, ops
-from .audio2text import Whisper, WhisperDecoder, WhisperEncoder
+from .audio2text import Whisper, WhisperDecoder, WhisperEncoder, WhisperPreprocessor
 from .image import ViT
 from .text import BERT, GPT, GPT2
 from .transformer import MHA, MLP, Decoder, DecoderLayer, Encoder, EncoderLayer
 
 __all__ = ["MHA", "MLP", "Encoder", "EncoderLayer", "Decoder", "DecoderLayer", "ViT", "WhisperEncoder", "WhisperDecoder",
-           "Whisper", "BERT", "GPT", "GPT2", "ops", "_lib"]
+           "Whisper", "WhisperPreprocessor", "BERT", "GPT", "GPT2", "ops", "_lib"]

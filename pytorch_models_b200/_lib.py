@@ -58,6 +58,8 @@ _SIGNATURES = {
     "b200enc_cls_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "b200enc_embed_rows": (
         c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200enc_whisper_logmel": (
+        c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200enc_time_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

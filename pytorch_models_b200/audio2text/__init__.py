@@ -1,3 +1,3 @@
-from .whisper import Whisper, WhisperDecoder, WhisperEncoder
+from .whisper import Whisper, WhisperDecoder, WhisperEncoder, WhisperPreprocessor
 
-__all__ = ["Whisper", "WhisperDecoder", "WhisperEncoder"]
+__all__ = ["Whisper", "WhisperDecoder", "WhisperEncoder", "WhisperPreprocessor"]

@@ -12,6 +12,7 @@ cross-attention to the encoder output, and one GEMM against the tied token table
 """
 from __future__ import annotations
 
+import math
 from types import SimpleNamespace
 
 import torch
@@ -202,3 +203,47 @@ class Whisper(nn.Module):
     def load_openai_state_dict(self, state_dict: dict) -> None:
         _load_openai(self.encoder, state_dict, "encoder")
         _load_openai(self.decoder, state_dict, "decoder")
+
+
+def mel_filters(n_mels: int, n_fft: int, sample_rate: float) -> Tensor:
+    """Triangular Slaney-style mel filter bank, (n_mels, n_fft // 2 + 1), area-normalised — the same definition as the
+    reference's ``get_mel_filters`` (audio/spectrogram.py:19-36): linear below 1 kHz (200/3 Hz per mel), logarithmic
+    above (step 6.4^(1/27))."""
+    f_max = sample_rate / 2
+    mel_max = f_max * 3 / 200 if f_max < 1000 else 15 + 27 * math.log(f_max / 1000, 6.4)
+    mels = torch.linspace(0, mel_max, n_mels + 2)
+    hz = torch.where(mels < 15, mels * 200 / 3, 1000 * 6.4 ** ((mels - 15) / 27))
+    fft_hz = torch.linspace(0, sample_rate / 2, n_fft // 2 + 1)
+    width = hz.diff()
+    ramp = hz.unsqueeze(1) - fft_hz.unsqueeze(0)
+    rising = -ramp[:-2] / width[:-1, None]
+    falling = ramp[2:] / width[1:, None]
+    bank = rising.minimum(falling).clamp(0)
+    bank *= 2 / (hz[2:, None] - hz[:-2, None])
+    return bank
+
+
+class WhisperPreprocessor(nn.Module):
+    """Reference ``WhisperPreprocessor`` (whisper.py:138-148): raw 16 kHz audio (N, L) -> normalised log-mel
+    (N, n_mels, L // 160). Same buffers as the reference (``window`` non-persistent, ``filters`` persistent); the
+    STFT, mel projection, log and dynamic-range normalisation run in one sm_100a kernel (fp32)."""
+
+    def __init__(self, variant: str = "tiny") -> None:
+        super().__init__()
+        n_mels = 128 if variant == "large-v3" else 80
+        self.n_fft, self.hop_length = 400, 160
+        self.register_buffer("window", torch.hann_window(self.n_fft), False)
+        self.register_buffer("filters", mel_filters(n_mels, self.n_fft, 16_000))
+        self._pf = _Packed()
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")
+        lead = x.shape[:-1]
+        L = x.shape[-1]
+        a = x.reshape(-1, L).float().contiguous()
+        ft = self._pf.get((self.filters,), lambda: SimpleNamespace(t=self.filters.detach().float().t().contiguous())).t
+        out = torch.empty(a.shape[0], ft.shape[1], L // self.hop_length, device=x.device, dtype=torch.float32)
+        ops.whisper_logmel(a, ft, out)
+        out = out.reshape(*lead, ft.shape[1], out.shape[-1])
+        return out if x.dtype == torch.float32 else out.to(x.dtype)

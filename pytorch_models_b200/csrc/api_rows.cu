@@ -1,7 +1,10 @@
 // C-ABI entry points for the HBM-bound row kernels: LayerNorm, row statistics, pooling, patch rows.
+#include <algorithm>
+
 #include "../../include/b200enc.h"
 #include "host_util.h"
 #include "layernorm.cuh"
+#include "logmel.cuh"
 #include "patchify.cuh"
 
 using namespace b200;
@@ -128,6 +131,27 @@ extern "C" int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, 
     time_rows_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), C, T, dst);
   else
     return set_error(-1, "b200enc_time_rows: unsupported dtype %d", dtype);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200enc_whisper_logmel(const float* audio, long long audio_stride, int N, int L, const float* filters_t,
+                                      int n_mels, float* out, int* sample_max, void* stream) {
+  B200_CHECK_ARG(audio && filters_t && out && sample_max, "b200enc_whisper_logmel: null pointer");
+  B200_CHECK_ARG(N >= 1 && L > LM_NFFT / 2 && audio_stride >= L,
+                 "b200enc_whisper_logmel: bad shape N=%d L=%d stride=%lld (reflect padding needs L > 200)", N, L,
+                 audio_stride);
+  B200_CHECK_ARG(n_mels >= 1 && n_mels <= LM_THREADS, "b200enc_whisper_logmel: n_mels=%d must be in [1, %d]", n_mels,
+                 LM_THREADS);
+  const int T = L / LM_HOP;  // torch.stft gives 1 + L / hop frames; the reference drops the last one
+  B200_CHECK_ARG(T >= 1, "b200enc_whisper_logmel: fewer than %d samples", LM_HOP);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  lm_init_max_kernel<<<(N + 255) / 256, 256, 0, s>>>(sample_max, N);
+  dim3 grid((T + LM_FRAMES - 1) / LM_FRAMES, N);
+  logmel_kernel<<<grid, LM_THREADS, 0, s>>>(audio, audio_stride, L, T, filters_t, n_mels, out, sample_max);
+  const long long per_sample = (long long)n_mels * T;
+  dim3 grid2(unsigned(std::min<long long>((per_sample + 255) / 256, 1024)), N);
+  logmel_finish_kernel<<<grid2, 256, 0, s>>>(out, per_sample, sample_max);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -272,3 +272,25 @@ def embed_rows(ids: Tensor, tok: Tensor, pos: Tensor, out: Tensor) -> Tensor:
         ids.data_ptr(), B * L, L, tok.data_ptr(), pos.data_ptr(), dt, vocab, d, out.data_ptr(), _stream()
     )
     return out
+
+
+def whisper_logmel(audio: Tensor, filters_t: Tensor, out: Tensor) -> Tensor:
+    """audio: (N, L) fp32, filters_t: (201, n_mels) fp32 (mel filter bank transposed) -> out (N, n_mels, L // 160) fp32:
+    the normalised log-mel spectrogram of ``WhisperPreprocessor`` (whisper.py:143-148)."""
+    _need_cuda(audio, filters_t, out)
+    _need(audio, torch.float32, "audio"), _need(filters_t, torch.float32, "filters_t"), _need(out, torch.float32, "out")
+    if audio.dim() != 2 or audio.stride(1) != 1 or not filters_t.is_contiguous() or not out.is_contiguous():
+        raise ValueError("whisper_logmel expects (N, L) audio with unit inner stride and contiguous filters / output")
+    N, L = audio.shape
+    n_mels = filters_t.shape[1]
+    if filters_t.shape[0] != 201 or out.shape != (N, n_mels, L // 160):
+        raise ValueError(f"shape mismatch: filters_t {tuple(filters_t.shape)}, out {tuple(out.shape)}, L={L}")
+    if N == 0:
+        return out
+    scratch = torch.empty(N, device=audio.device, dtype=torch.int32)
+    _call(
+        "b200enc_whisper_logmel", None,
+        audio.data_ptr(), audio.stride(0), N, L, filters_t.data_ptr(), n_mels, out.data_ptr(), scratch.data_ptr(),
+        _stream()
+    )
+    return out

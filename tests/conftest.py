@@ -15,6 +15,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 FIXTURES = ["vit_cls", "vit_gap", "vit_siglip", "vit_p14", "vit_long", "whisper", "bert",
             "decoder_postnorm_cross", "decoder_causal_long", "whisper_full", "gpt2", "gpt"]
+AUDIO_FIXTURES = ["logmel_tiny", "logmel_large_v3"]  # fp32 front end: own (much tighter) tolerance
 
 
 def pytest_configure(config):
@@ -67,6 +68,8 @@ def build_model(g: Golden):
         m = pm.Decoder(h["n_layers"], h["d_model"], cross_attn=h["cross_attn"], pre_norm=h["pre_norm"])
     elif kind == "whisper_full":
         m = pm.Whisper(h["vocab_size"], h["n_layers"], h["d_model"], h["n_mels"])
+    elif kind == "logmel":
+        m = pm.WhisperPreprocessor(h["variant"])
     elif kind in ("gpt2", "gpt"):
         base = pm.GPT2 if kind == "gpt2" else pm.GPT
         # vocab_size is a class attribute, as in the reference (gpt2.py:12, gpt.py:15)

@@ -22,7 +22,7 @@ import torch
 sys.path.insert(0, "/root/reference")
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 
-from pytorch_models.audio2text.whisper import Whisper, WhisperEncoder  # noqa: E402
+from pytorch_models.audio2text.whisper import Whisper, WhisperEncoder, WhisperPreprocessor  # noqa: E402
 from pytorch_models.image import ViT  # noqa: E402
 from pytorch_models.text import BERT, GPT, GPT2  # noqa: E402
 from pytorch_models.transformer import Decoder  # noqa: E402
@@ -92,6 +92,7 @@ def main() -> None:
     save("bert", b, dict(kind="bert", vocab_size=1000, n_layers=2, d_model=128), t, dict(tokens=b(t)))
 
     decoder_cases()
+    audio_cases()
 
     # C1 = BASELINE configs[0]: ViT-Ti/16 augreg 224, batch 8, random-init weights, fp32 CPU forward (reference path)
     torch.manual_seed(0)
@@ -146,8 +147,23 @@ def decoder_cases() -> None:
         save(name, m, dict(kind=name, vocab_size=777, n_layers=2, d_model=64), t, dict(logits=m(t)))
 
 
+def audio_cases() -> None:
+    """the Whisper audio front end (whisper.py:138-148, audio/spectrogram.py)."""
+    torch.manual_seed(13)
+    for name, variant, shape in (("logmel_tiny", "tiny", (2, 16000)), ("logmel_large_v3", "large-v3", (1, 3333))):
+        pre = WhisperPreprocessor(variant).eval()
+        t = torch.arange(shape[1]) / 16000.0
+        x = 0.1 * torch.randn(shape) + 0.5 * torch.sin(2 * torch.pi * 440.0 * t) * torch.linspace(0, 1, shape[1])
+        x[0, : shape[1] // 5] = 0.0  # a stretch of digital silence: log10(0) = -inf meets the max - 8 floor
+        save(name, pre, dict(kind="logmel", variant=variant), x, dict(logmel=pre(x)))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "decoder":  # add the decoder fixtures without rewriting the others
+    if len(sys.argv) > 1 and sys.argv[1] == "audio":
+        with torch.no_grad():
+            torch.set_num_threads(8)
+            audio_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "decoder":  # add the decoder fixtures without rewriting the others
         with torch.no_grad():
             torch.set_num_threads(8)
             decoder_cases()

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FIXTURES, build_model, error_stats
+from conftest import AUDIO_FIXTURES, FIXTURES, build_model, error_stats
 from oracle import oracle_torch
 
 pytestmark = pytest.mark.gpu
@@ -221,3 +221,36 @@ def test_decoder_generator_greedy_matches_oracle(golden):
                 nxt = got[5 + step]
             want.append(nxt)
     assert want == got
+
+
+@pytest.mark.parametrize("name", AUDIO_FIXTURES)
+def test_whisper_preprocessor_against_reference_golden(golden, name):
+    """fp32 front end (STFT + mel + log + normalisation in one kernel): absolute tolerance 2e-4 on values in [-0.6, 1.5]
+    (direct 400-point DFT vs the reference's FFT: different summation order, nothing else)."""
+    g = golden(name)
+    m = build_model(g).cuda()
+    x = torch.from_numpy(np.array(g.input)).cuda()
+    with torch.no_grad():
+        got = m(x)
+    assert got.dtype == torch.float32 and tuple(got.shape) == g.out["logmel"].shape
+    np.testing.assert_allclose(got.cpu().numpy(), g.out["logmel"], rtol=0, atol=2e-4)
+    # leading dims and strided input are accepted like any (*, L) tensor
+    with torch.no_grad():
+        again = m(x.unsqueeze(0))[0]
+    assert torch.equal(again, got)
+
+
+def test_whisper_audio_to_encoder_end_to_end():
+    """Raw audio -> WhisperPreprocessor -> WhisperEncoder on the GPU against the fp32 oracle chain (30 s would be
+    480000 samples; 2 s here)."""
+    import pytorch_models_b200 as pm
+
+    torch.manual_seed(0)
+    pre, enc = pm.WhisperPreprocessor("tiny"), pm.WhisperEncoder(2, 128, 80).eval()
+    sd = oracle_torch.randomize_(enc.state_dict(), 100)
+    audio = 0.3 * torch.randn(2, 32000)
+    with torch.no_grad():
+        want = oracle_torch.whisper_encoder_forward(sd, oracle_torch.whisper_logmel(audio, pre.filters))
+        got = enc.cuda()(pre.cuda()(audio.cuda())).float().cpu()
+    max_abs, min_cos = error_stats(got.numpy(), want.numpy())
+    assert max_abs <= MAX_ABS_12 and min_cos >= MIN_COS, (max_abs, min_cos)

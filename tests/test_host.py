@@ -213,3 +213,14 @@ def test_decoder_modules_mirror_reference_structure():
     assert pm.WhisperDecoder.max_seq_len == 448
     m = pm.Whisper.from_openai("tiny")
     assert m.decoder.token_embs.weight.shape == (51865, 384) and len(m.decoder.layers) == 4
+
+
+def test_whisper_preprocessor_mirrors_reference_buffers(golden):
+    """Same buffers as the reference (filters persistent, window not), identical filter bank values, CPU input raises."""
+    g = golden("logmel_large_v3")
+    m = pm.WhisperPreprocessor("large-v3")
+    assert list(m.state_dict().keys()) == ["filters"] and m.window.shape == (400,)
+    np.testing.assert_array_equal(m.filters.numpy(), g.sd["filters"])
+    assert pm.WhisperPreprocessor().filters.shape == (80, 201)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1600))

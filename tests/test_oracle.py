@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FIXTURES, Golden
+from conftest import AUDIO_FIXTURES, FIXTURES, Golden
 from oracle import oracle_np, oracle_torch
 
 TOL = 2e-5
@@ -110,3 +110,16 @@ def test_oracle_edge_cases():
             a = oracle_np.encoder(sd, x, h, pre, 1e-5)
             b = oracle_torch.encoder(sd_t, torch.from_numpy(x), h, pre, 1e-5).numpy()
             np.testing.assert_allclose(a, b, rtol=TOL, atol=TOL)
+
+
+@pytest.mark.parametrize("name", AUDIO_FIXTURES)
+def test_logmel_oracles_match_reference(golden, name):
+    """WhisperPreprocessor (whisper.py:138-148): numpy restatement (explicit framing + rfft) and the torch.stft one
+    against the reference's output, including a stretch of digital silence (log10(0) = -inf under the max - 8 floor)."""
+    g = golden(name)
+    want = g.out["logmel"]
+    got_np = oracle_np.whisper_logmel(g.input, g.sd["filters"])
+    np.testing.assert_allclose(got_np, want, rtol=0, atol=2e-5)
+    got_t = oracle_torch.whisper_logmel(torch.from_numpy(np.array(g.input)), torch.from_numpy(np.array(g.sd["filters"])))
+    np.testing.assert_allclose(got_t.numpy(), want, rtol=0, atol=2e-5)
+    assert want.shape == (g.input.shape[0], g.sd["filters"].shape[0], g.input.shape[1] // 160)
