@@ -25,6 +25,8 @@ const char* b200enc_last_error(void);
 /* flags for b200enc_linear */
 #define B200ENC_LINEAR_GELU 1          /* exact (erf) GELU after bias: nn.GELU(), transformer.py:61 */
 #define B200ENC_LINEAR_GELU_TANH 2     /* tanh GELU after bias: nn.GELU(approximate="tanh"), transformer.py:62 (no residual) */
+#define B200ENC_LINEAR_RELU 4          /* nn.ReLU, transformer.py:63 (no residual) */
+#define B200ENC_LINEAR_SILU 8          /* nn.SiLU, transformer.py:64 (no residual) */
 #define B200ENC_LINEAR_DIRECT_STORE 256 /* debug: per-thread st.global epilogue without the smem transpose */
 #define B200ENC_LINEAR_ONE_CTA 512      /* debug: 128-row tiles on single CTAs instead of 256-row tiles on CTA pairs */
 

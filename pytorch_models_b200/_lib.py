@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libb200enc.so")
 
 LINEAR_GELU = 1
 LINEAR_GELU_TANH = 2
+LINEAR_RELU = 4
+LINEAR_SILU = 8
 ATTN_CAUSAL = 1
 LINEAR_DIRECT_STORE = 256
 DTYPE_BF16 = 0

@@ -56,7 +56,11 @@ int dispatch_epilogue(int sel, bool tma, bool stats, const CUtensorMap& ta, cons
     case 7: return dispatch_store<kCtas, true, 1, true>(tma, stats, ta, tb, tc, p, grid, s);
     case 8: return dispatch_store<kCtas, false, 2, false>(tma, stats, ta, tb, tc, p, grid, s);   // tanh-GELU
     case 12: return dispatch_store<kCtas, true, 2, false>(tma, stats, ta, tb, tc, p, grid, s);   // LN fold + tanh-GELU
-    default: return set_error(-1, "b200enc_linear: tanh-GELU cannot be combined with a residual");
+    case 16: return dispatch_store<kCtas, false, 3, false>(tma, stats, ta, tb, tc, p, grid, s);  // ReLU
+    case 20: return dispatch_store<kCtas, true, 3, false>(tma, stats, ta, tb, tc, p, grid, s);
+    case 32: return dispatch_store<kCtas, false, 4, false>(tma, stats, ta, tb, tc, p, grid, s);  // SiLU
+    case 36: return dispatch_store<kCtas, true, 4, false>(tma, stats, ta, tb, tc, p, grid, s);
+    default: return set_error(-1, "b200enc_linear: tanh-GELU / ReLU / SiLU cannot be combined with a residual");
   }
 }
 
@@ -89,7 +93,10 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const bool fold = a->colsum != nullptr;
   const bool gelu = (a->flags & B200ENC_LINEAR_GELU) != 0;
   const bool gelu_tanh = (a->flags & B200ENC_LINEAR_GELU_TANH) != 0;
-  B200_CHECK_ARG(!(gelu && gelu_tanh), "b200enc_linear: GELU and GELU_TANH are mutually exclusive");
+  const bool relu = (a->flags & B200ENC_LINEAR_RELU) != 0;
+  const bool silu = (a->flags & B200ENC_LINEAR_SILU) != 0;
+  B200_CHECK_ARG(int(gelu) + int(gelu_tanh) + int(relu) + int(silu) <= 1,
+                 "b200enc_linear: at most one activation flag may be set");
   const bool res = a->residual != nullptr;
   const bool tma_store = (a->flags & B200ENC_LINEAR_DIRECT_STORE) == 0;
   const bool stats = a->stats_out != nullptr;
@@ -136,7 +143,7 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const int slots = sm_count() / ctas;  // CTAs (or CTA pairs) resident at once: the kernel is persistent
   const int grid = int(total < slots ? total : slots) * ctas;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int sel = (gelu_tanh ? 8 : 0) | (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
+  const int sel = (silu ? 32 : 0) | (relu ? 16 : 0) | (gelu_tanh ? 8 : 0) | (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
   if (ctas == 2) return dispatch_epilogue<2>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
   return dispatch_epilogue<1>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
 }

@@ -2,7 +2,7 @@
 //
 //   warp 0      : TMA producer (A/W tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
-//   warps 2..9  : epilogue (tcgen05.ld -> registers -> bias / LayerNorm-fold / erf-GELU / residual -> bf16 ->
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> bias / LayerNorm-fold / activation / residual -> bf16 ->
 //                 swizzled smem -> TMA store), overlapped with the next tile's main loop through two
 //                 256-column TMEM accumulators. Two warps per TMEM lane quarter, each owning 128 of the 256
 //                 columns, so every SM sub-partition has two epilogue warps to hide latencies with.
@@ -10,7 +10,7 @@
 // kCtas == 2 runs the same roles on a CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x 256 x 16 MMA spans both
 // SMs, each CTA stages only its 128 rows of A and its 128 rows of W, so the L2 -> SM operand traffic per FLOP drops by a
 // third (the 1-CTA tile needs 96 B/clk/SM at full tensor rate, more than the ~64 B/clk an SM can pull from L2) and the
-// same 192 KB of smem holds 6 instead of 4 pipeline stages.
+// same smem holds 5 instead of 3 pipeline stages.
 //
 // This one kernel serves every linear on the encoder path (reference call sites: transformer.py:47-49 fused QKV,
 // transformer.py:53 out_proj, transformer.py:59-67 MLP, vit.py:78 patch embedding as a GEMM over patch rows).
@@ -34,7 +34,7 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 32 * 128;  // one staging buffer: 32 rows x 64 bf16
 constexpr int GEMM_SMEM_COLVEC = GEMM_EPI_WARPS * 2 * 128 * 4;  // per warp: bias|c and colsum of its 128 columns
 // smem plan: kCtas == 1: 3 stages x 48 KB + 1 staging buffer per epilogue warp (only used for problems of <= 128 rows)
-//            kCtas == 2: 4 stages x 32 KB + 2 staging buffers per epilogue warp (store drain never on the critical path)
+//            kCtas == 2: 5 stages x 32 KB + 1 staging buffer per epilogue warp (measured equal to 4 stages + 2 buffers)
 template <int kCtas>
 struct GemmSmem {
   static constexpr int kStages = kCtas == 2 ? GEMM_STAGES_2CTA : 3;
@@ -98,7 +98,14 @@ __device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
   return make_float2(x.x * __frcp_rn(den.x), x.y * __frcp_rn(den.y));
 }
 
-// kAct: 0 = none, 1 = erf-GELU, 2 = tanh-GELU
+// SiLU (nn.SiLU, transformer.py:64): x * sigmoid(x) = x / (1 + 2^(-x log2 e)); one MUFU.EX2 and one MUFU.RCP per element.
+__device__ __forceinline__ float2 silu_fast2(float2 x) {
+  const float2 w = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 den = __fadd2_rn(make_float2(fast_exp2(w.x), fast_exp2(w.y)), make_float2(1.0f, 1.0f));
+  return make_float2(x.x * __frcp_rn(den.x), x.y * __frcp_rn(den.y));
+}
+
+// kAct: 0 = none, 1 = erf-GELU, 2 = tanh-GELU, 3 = ReLU, 4 = SiLU
 template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -360,6 +367,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             x[u] = kFold ? __ffma2_rn(rstd2, a, __ffma2_rn(nmr2, cs2, cb2)) : __fadd2_rn(a, cb2);
             if (kAct == 1) x[u] = gelu_erf_fast2(x[u]);
             if (kAct == 2) x[u] = gelu_tanh_fast2(x[u]);
+            if (kAct == 3) x[u] = make_float2(fmaxf(x[u].x, 0.0f), fmaxf(x[u].y, 0.0f));
+            if (kAct == 4) x[u] = silu_fast2(x[u]);
             if (kRes) {
               const uint32_t rr = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + u];
               x[u] = __fadd2_rn(x[u], make_float2(bf16_lo(rr), bf16_hi(rr)));

@@ -126,7 +126,7 @@ struct LinearCase {
   const char* name;
   int batches, M, N, K;
   bool fold;
-  int gelu;  // 0 none, 1 erf, 2 tanh
+  int gelu;  // activation: 0 none, 1 erf-GELU, 2 tanh-GELU, 3 ReLU, 4 SiLU
   bool res, res_bcast, direct, ints;
   int out_row_off;  // output rows shifted by this inside a (M + off)-row batch (patch-embed layout)
   int check_rows;   // rows per batch checked on the CPU (0 = all)
@@ -169,7 +169,7 @@ static bool run_linear(const LinearCase& c) {
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));  // sentinel 0x7f7f = 3.39e38 in bf16
 
   const int dbg = getenv("B200_DEBUG_FLAGS") ? atoi(getenv("B200_DEBUG_FLAGS")) : 0;  // timing experiments only
-  const int flags = (c.gelu == 1 ? B200ENC_LINEAR_GELU : c.gelu == 2 ? B200ENC_LINEAR_GELU_TANH : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
+  const int flags = (c.gelu == 1 ? B200ENC_LINEAR_GELU : c.gelu == 2 ? B200ENC_LINEAR_GELU_TANH : c.gelu == 3 ? B200ENC_LINEAR_RELU : c.gelu == 4 ? B200ENC_LINEAR_SILU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
   const int n_slices = (N + 127) / 128;
   const bool want_stats = c.res && !c.fold && !c.direct;
   GuardedBuf gso(size_t(B) * M * n_slices * 8);
@@ -222,6 +222,8 @@ static bool run_linear(const LinearCase& c) {
         }
         if (c.gelu == 1) v = gelu_ref(v);
         if (c.gelu == 2) v = gelu_tanh_ref(v);
+        if (c.gelu == 3) v = v > 0 ? v : 0;
+        if (c.gelu == 4) v = v / (1.0 + exp(-v));
         if (c.res) v += bf2f(hr[(c.res_bcast ? size_t(m) : size_t(b) * M + m) * N + n]);
         const float got = bf2f(ho[(size_t(b) * Mo + c.out_row_off + m) * N + n]);
         cmp_one(st, v, got, c.ints ? 1e-6 : 0.02, c.ints ? 0.0 : 0.01, b * M + m, n, c.name);
@@ -294,6 +296,8 @@ static const LinearCase kLinearCases[] = {
     {"fold_gelu", 1, 1000, 3072, 768, true, true, false, false, false, false, 0, 60, 0},
     {"fold_gelu_tanh", 1, 1000, 3072, 768, true, 2, false, false, false, false, 0, 60, 0},
     {"gelu_tanh", 2, 300, 512, 256, false, 2, false, false, false, false, 0, 60, 0},
+    {"relu", 2, 300, 512, 256, false, 3, false, false, false, false, 0, 60, 0},
+    {"fold_silu", 1, 1000, 1024, 512, true, 4, false, false, false, false, 0, 60, 0},
     {"residual", 1, 1000, 768, 3072, false, false, true, false, false, false, 0, 60, 0},
     {"fold_qkv", 1, 1000, 2304, 768, true, false, false, false, false, false, 0, 60, 0},
     {"perf_qkv", 1, 25216, 2304, 768, true, false, false, false, false, false, 0, 16, 20},

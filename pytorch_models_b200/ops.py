@@ -78,7 +78,8 @@ def linear(
 ) -> Tensor:
     """out[b, m, :] = epilogue(x[b, m, :] @ w.T); x, out, residual are (batches, M, *) views with unit inner stride.
 
-    ``gelu``: False, True (exact erf form) or "tanh" (``nn.GELU(approximate="tanh")``; not with a residual).
+    ``gelu`` selects the activation: False, True (exact erf GELU), "tanh" (``nn.GELU(approximate="tanh")``), "relu" or
+    "silu" (the last three not together with a residual).
     A residual with a leading dimension of 1 is broadcast over the batch (positional embedding).
     ``rowstats`` is either (batches*M, 2) = (mean, rstd) from `row_stats`, or (batches*M, parts, 2) partial
     (mean, M2) per 128 input columns as written through ``stats_out`` by the linear that produced ``x``
@@ -111,9 +112,12 @@ def linear(
         parts = 0 if rowstats.dim() == 2 else rowstats.shape[1]
     if stats_out is not None and (not stats_out.is_contiguous() or stats_out.numel() != 2 * batches * M * ((N + 127) // 128)):
         raise ValueError("stats_out must be a contiguous (batches*M, ceil(N/128), 2) tensor")
-    if gelu not in (False, True, "tanh"):
-        raise ValueError(f"gelu must be False, True or 'tanh', got {gelu!r}")
-    act = _lib.LINEAR_GELU_TANH if gelu == "tanh" else (_lib.LINEAR_GELU if gelu else 0)
+    acts = {False: 0, True: _lib.LINEAR_GELU, "tanh": _lib.LINEAR_GELU_TANH, "relu": _lib.LINEAR_RELU,
+            "silu": _lib.LINEAR_SILU}
+    if isinstance(gelu, (bool, str)) and gelu in acts:
+        act = acts[gelu]
+    else:
+        raise ValueError(f"gelu must be False, True, 'tanh', 'relu' or 'silu', got {gelu!r}")
     flags = act | (_lib.LINEAR_DIRECT_STORE if direct_store else 0)
     args = _lib.LinearArgs(
         x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum),

@@ -17,7 +17,7 @@ hand-written sm_100a kernels from ``libb200enc.so``:
     over the residual stream is needed after the first layer.
 
 Only what the kernels implement is accepted (self/cross attention, optionally causal, no attn_bias; head_dim 64;
-erf or tanh GELU; eval mode);
+GELU (erf / tanh), ReLU, SiLU; eval mode);
 anything else raises ``NotImplementedError`` — there is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -226,16 +226,13 @@ class MLP(nn.Sequential):
         self._p1, self._p2 = _Packed(), _Packed()
 
     def check_supported(self) -> None:
-        if self._act_name not in ("gelu", "approximate_gelu"):
-            raise NotImplementedError(
-                f"act={self._act_name!r}: only GELU (exact erf or tanh form) is fused into the sm_100a GEMM epilogue")
         if self.training and self.dropout.p > 0.0:
             raise NotImplementedError("MLP dropout (training mode) is not supported; call .eval()")
 
     @property
     def gelu_mode(self) -> bool | str:
-        """Epilogue selector of `ops.linear`: exact erf GELU, or the tanh form for ``act="approximate_gelu"``."""
-        return "tanh" if self._act_name == "approximate_gelu" else True
+        """Epilogue selector of `ops.linear` for the reference's four activations (transformer.py:60-65)."""
+        return {"gelu": True, "approximate_gelu": "tanh", "relu": "relu", "silu": "silu"}[self._act_name]
 
     def pack1(self, norm: nn.LayerNorm | None) -> SimpleNamespace:
         lin = self.linear1

@@ -123,6 +123,41 @@ def test_linear_tanh_gelu(fold):
         ops.linear(x, w, b, out, gelu="tanh", residual=out.clone())
 
 
+@pytest.mark.parametrize("act", ["gelu", "approximate_gelu", "relu", "silu"])
+@pytest.mark.parametrize("pre_norm", [True, False])
+def test_mlp_and_layer_activations(act, pre_norm):
+    """All four activations of the reference MLP (transformer.py:60-65), stand-alone and inside a layer (folded
+    LayerNorm for pre-norm), against the same modules in fp32 PyTorch."""
+    import pytorch_models_b200 as pm
+
+    torch.manual_seed(0)
+    d = 128
+    layer = pm.EncoderLayer(d, act=act, pre_norm=pre_norm).eval()
+    ref_act = {"gelu": lambda t: F.gelu(t), "approximate_gelu": lambda t: F.gelu(t, approximate="tanh"),
+               "relu": F.relu, "silu": F.silu}[act]
+    x = torch.randn(3, 50, d)
+    mlp = layer.mlp
+    want = mlp.linear2(ref_act(mlp.linear1(x)))
+    with torch.no_grad():
+        got = mlp.cuda()(x.cuda()).cpu()
+    _close(got, want.detach(), 0.02, 0.02)
+    # whole layer: reference arithmetic in fp32 on the CPU copy of the same parameters
+    layer = layer.cpu()
+    with torch.no_grad():
+        def mha(t):
+            q, k, v = (getattr(layer.sa, n)(t).unflatten(-1, (2, 64)).transpose(1, 2) for n in ("q_proj", "k_proj", "v_proj"))
+            return layer.sa.out_proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).flatten(-2))
+        ff = lambda t: mlp.linear2(ref_act(mlp.linear1(t)))  # noqa: E731
+        if pre_norm:
+            h = x + mha(layer.sa_norm(x))
+            want = h + ff(layer.mlp_norm(h))
+        else:
+            h = layer.sa_norm(x + mha(x))
+            want = layer.mlp_norm(h + ff(h))
+        got = layer.cuda()(x.cuda()).cpu()
+    _close(got, want, 0.05, 0.02)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_embed_rows(dtype):
     from pytorch_models_b200 import ops
@@ -191,7 +226,7 @@ def test_bad_arguments_raise():
         ops.attention(q, q, q, torch.empty_like(q), 3, 1.0)
 
 
-@pytest.mark.parametrize("case", ["linear:tails_tma", "linear:embed_like", "linear:fold_gelu", "linear:fold_gelu_tanh",
+@pytest.mark.parametrize("case", ["linear:tails_tma", "linear:embed_like", "linear:fold_gelu", "linear:fold_gelu_tanh", "linear:relu", "linear:fold_silu",
                                   "attn:l197_tmem", "attn:cross_q1", "attn:causal_l448", "attn:causal_many", "rows:all"])
 def test_native_selftest(case):
     """The stand-alone C++ harness (fp64 CPU check inside the binary) on its edge-case shapes."""
