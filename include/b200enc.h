@@ -124,6 +124,18 @@ int b200enc_patch_rows(const void* img, int img_dtype, int B, int H, int W, int 
 int b200enc_cls_rows(const void* cls, int B, int d, void* tokens, long long batch_stride, void* stream);
 
 /*
+ * b200enc_attention with an additive bias: softmax_j(scale * q_i . k_j + bias[b][h][i][j]) — the `attn_bias` argument
+ * of MHA.forward (transformer.py:41,52: SDPA's attn_mask; T5's relative position bias). bias is fp32 with element
+ * strides (batch, head, query row); a stride of 0 broadcasts over that dimension, consecutive keys are contiguous.
+ * -inf entries mask a key. May be combined with B200ENC_ATTN_CAUSAL. The bias is read straight from global memory
+ * by the softmax threads (one row each): correct for any shape, but slower than the unbiased kernel.
+ */
+int b200enc_attention_bias(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                           long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
+                           int H, int Lq, int Lkv, int head_dim, float scale, int flags, const float* bias,
+                           long long bias_b_stride, long long bias_h_stride, long long bias_row_stride, void* stream);
+
+/*
  * Token + position embedding: out[r][:] = bf16(tok[ids[r]][:] + pos[r % L][:]) for r < rows (= batch * L).
  * Replaces `self.token_embs(x) + self.pos_embs[:L]` (text/bert.py:35-36, text/gpt2.py:22-23, text/gpt.py:25-26,
  * audio2text/whisper.py:47-48). ids: int64 device pointer; tok [vocab, d] and pos [>= L, d] contiguous, both `dtype`

@@ -20,8 +20,9 @@ def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def mha(sd: dict, prefix: str, q_in: Tensor, kv_in: Tensor | None, n_heads: int, causal: bool = False) -> Tensor:
-    """MHA.forward (transformer.py:36-53), k = v = kv_in (self-attention when None), attn_bias None."""
+def mha(sd: dict, prefix: str, q_in: Tensor, kv_in: Tensor | None, n_heads: int, causal: bool = False,
+        attn_bias: Tensor | None = None) -> Tensor:
+    """MHA.forward (transformer.py:36-53), k = v = kv_in (self-attention when None)."""
     kv_in = q_in if kv_in is None else kv_in
 
     def proj(name: str, t: Tensor) -> Tensor:
@@ -29,7 +30,7 @@ def mha(sd: dict, prefix: str, q_in: Tensor, kv_in: Tensor | None, n_heads: int,
         return y.unflatten(-1, (n_heads, -1)).transpose(-2, -3)
 
     o = F.scaled_dot_product_attention(proj("q_proj", q_in), proj("k_proj", kv_in), proj("v_proj", kv_in),
-                                       is_causal=causal)
+                                       attn_mask=attn_bias, is_causal=causal)
     return F.linear(o.transpose(-2, -3).flatten(-2), sd[prefix + "out_proj.weight"], sd.get(prefix + "out_proj.bias"))
 
 

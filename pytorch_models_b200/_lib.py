@@ -49,6 +49,11 @@ _SIGNATURES = {
         [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int,
          c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     ),
+    "b200enc_attention_bias": (
+        c_int,
+        [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int,
+         c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p],
+    ),
     "b200enc_layernorm": (
         c_int,
         [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p],

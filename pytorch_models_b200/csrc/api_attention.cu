@@ -14,17 +14,23 @@ extern "C" void b200enc_debug_attention_trace(long long* buf) { g_attention_trac
 namespace {
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                      const AttnParams& p, cudaStream_t s) {
-  B200_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
+  if (p.bias != nullptr) {
+    B200_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
+  }
   B200_CUDA(cudaGetLastError());
   return 0;
 }
 }  // namespace
 
-extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
-                                 long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo,
-                                 int B, int H, int Lq, int Lkv, int head_dim, float scale, int flags, void* stream) {
+static int attention_impl(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                          long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
+                          int H, int Lq, int Lkv, int head_dim, float scale, int flags, const float* bias,
+                          long long bias_b_stride, long long bias_h_stride, long long bias_row_stride, void* stream) {
   B200_CHECK_ARG(q && k && v && out, "b200enc_attention: null tensor pointer");
   B200_CHECK_ARG(head_dim == ATT_HD, "b200enc_attention: head_dim=%d is not supported (only 64)", head_dim);
   B200_CHECK_ARG(B >= 1 && H >= 1 && Lq >= 1 && Lkv >= 1, "b200enc_attention: bad shape B=%d H=%d Lq=%d Lkv=%d", B, H,
@@ -55,6 +61,10 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
   p.out_batch_stride = out_batch_stride;
   p.ldo = ldo;
   p.causal = (flags & B200ENC_ATTN_CAUSAL) ? 1 : 0;
+  p.bias = bias;
+  p.bias_b_stride = bias_b_stride;
+  p.bias_h_stride = bias_h_stride;
+  p.bias_row_stride = bias_row_stride;
 #ifdef ATT_TRACE
   p.trace = g_attention_trace;
 #else
@@ -62,4 +72,23 @@ extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ld
 #endif
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return launch_attention(tq, tk, tv, to, p, s);
+}
+
+extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                                 long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo,
+                                 int B, int H, int Lq, int Lkv, int head_dim, float scale, int flags, void* stream) {
+  return attention_impl(q, q_batch_stride, ldq, k, v, kv_batch_stride, ldkv, out, out_batch_stride, ldo, B, H, Lq, Lkv,
+                        head_dim, scale, flags, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int b200enc_attention_bias(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                                      long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride,
+                                      int ldo, int B, int H, int Lq, int Lkv, int head_dim, float scale, int flags,
+                                      const float* bias, long long bias_b_stride, long long bias_h_stride,
+                                      long long bias_row_stride, void* stream) {
+  B200_CHECK_ARG(bias != nullptr, "b200enc_attention_bias: null bias");
+  B200_CHECK_ARG(bias_b_stride >= 0 && bias_h_stride >= 0 && bias_row_stride >= 0,
+                 "b200enc_attention_bias: negative bias stride");
+  return attention_impl(q, q_batch_stride, ldq, k, v, kv_batch_stride, ldkv, out, out_batch_stride, ldo, B, H, Lq, Lkv,
+                        head_dim, scale, flags, bias, bias_b_stride, bias_h_stride, bias_row_stride, stream);
 }

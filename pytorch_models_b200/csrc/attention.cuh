@@ -47,6 +47,10 @@ struct AttnParams {
   __nv_bfloat16* out; // [B, Lq, ldo] with head h at columns [64h, 64h+64)
   long long out_batch_stride;
   int ldo;
+  // additive attention bias (attn_bias / attn_mask of SDPA), fp32, element strides; nullptr = none. Strides of 0
+  // broadcast over batch / head; the innermost (key) stride is 1.
+  const float* bias;
+  long long bias_b_stride, bias_h_stride, bias_row_stride;
   long long* trace;   // debug only: (event, clock) records of CTA 0 (nullptr in production)
 };
 
@@ -70,13 +74,31 @@ struct AttnParams {
 // valid columns; `masked` (warp-uniform): the block has a partial last chunk or holds the causal diagonal — columns
 // >= lim are set to -inf before the maximum, after which the exponential pass needs no predicates.
 // (One copy of this code on purpose: two inlined specialisations made ptxas spill the 128-register row.)
+// kBias: x = s * c + bias * log2(e) is formed right after the load (bias_row points at this row's bias for the
+// block's first column, n_cols = valid columns of the block) and the rest runs with c = 1.
+template <bool kBias>
 __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool masked, int lim, float c, float& m,
-                                              float& l, float& alpha, bool& rescale) {
+                                              float& l, float& alpha, bool& rescale, const float* bias_row = nullptr,
+                                              int n_cols = 0) {
   uint32_t v[4][32];
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch)
     if (ch < n_chunks) tmem_ld32(tS + ch * 32, v[ch]);
   tmem_wait_ld();
+  if (kBias) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < n_chunks) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = ch * 32 + i;
+          const float bv = col < n_cols ? __ldg(bias_row + col) : 0.0f;
+          v[ch][i] = __float_as_uint(fmaf(__uint_as_float(v[ch][i]), c, bv * 1.4426950408889634f));
+        }
+      }
+    }
+    c = 1.0f;
+  }
   if (masked) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
@@ -126,6 +148,7 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
   l += sum.x + sum.y;
 }
 
+template <bool kBias>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -362,7 +385,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         bool rescale = false;
         if (warp_live) {
           const bool masked = diag || (nvalid & 31) != 0;
-          softmax_block(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
+          if (kBias) {
+            const float* brow = p.bias + (long long)b * p.bias_b_stride + (long long)h * p.bias_h_stride +
+                                (long long)min(qrow, p.Lq - 1) * p.bias_row_stride + j * ATT_BKV;
+            softmax_block<true>(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale, brow, nvalid);
+          } else {
+            softmax_block<false>(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
+          }
         }
         if (j > 0 && rescale) {  // warp-uniform
           // P.V(j-1) must have landed before O is rescaled. The parity wait is safe although most blocks skip it:

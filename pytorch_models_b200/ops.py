@@ -131,10 +131,13 @@ def linear(
     return out
 
 
-def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, causal: bool = False) -> Tensor:
+def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, causal: bool = False,
+              bias: Tensor | None = None) -> Tensor:
     """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64).
 
-    ``causal``: query i sees keys 0..i (top-left aligned like ``F.scaled_dot_product_attention(is_causal=True)``)."""
+    ``causal``: query i sees keys 0..i (top-left aligned like ``F.scaled_dot_product_attention(is_causal=True)``).
+    ``bias``: fp32 (B, H, Lq, Lkv) view added to the scaled scores (``attn_mask`` of SDPA); broadcast dimensions may
+    have stride 0 (``Tensor.expand``), the last stride must be 1."""
     _need_cuda(q, k, v, out)
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, name)
@@ -146,6 +149,19 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
         raise ValueError("width not divisible by n_heads")
     if k.shape != v.shape or k.stride() != v.stride() or k.shape[0] != B or k.shape[2] != D or out.shape != q.shape:
         raise ValueError("q/k/v/out shapes or strides are inconsistent")
+    if bias is not None:
+        _need_cuda(bias)
+        _need(bias, torch.float32, "bias")
+        if bias.shape != (B, n_heads, Lq, Lkv) or (Lkv > 1 and bias.stride(3) != 1) or min(bias.stride()) < 0:
+            raise ValueError(f"bias must be a (B, H, Lq, Lkv) = {(B, n_heads, Lq, Lkv)} view with unit inner stride")
+        _call(
+            "b200enc_attention_bias", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal), bias=True),
+            q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1),
+            out.data_ptr(), out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
+            _lib.ATTN_CAUSAL if causal else 0, bias.data_ptr(), bias.stride(0), bias.stride(1), bias.stride(2),
+            _stream(),
+        )
+        return out
     _call(
         "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal)),
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),

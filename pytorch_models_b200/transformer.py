@@ -16,7 +16,7 @@ hand-written sm_100a kernels from ``libb200enc.so``:
     its input (per-128-column (mean, M2) partials, combined in a fixed order by the consumer), so no separate pass
     over the residual stream is needed after the first layer.
 
-Only what the kernels implement is accepted (self/cross attention, optionally causal, no attn_bias; head_dim 64;
+Only what the kernels implement is accepted (self/cross attention, optionally causal and/or with attn_bias; head_dim 64;
 GELU (erf / tanh), ReLU, SiLU; eval mode);
 anything else raises ``NotImplementedError`` — there is no PyTorch fallback.
 """
@@ -142,12 +142,25 @@ class MHA(nn.Module):
         return self._packs[name].get(params, lambda: pack_plain(linears))
 
     def check_supported(self, attn_bias: Tensor | None = None, causal: bool = False) -> None:
-        if attn_bias is not None:
-            raise NotImplementedError("attn_bias is not supported by the sm_100a attention kernel")
         if self.head_dim != _SUPPORTED_HEAD_DIM:
             raise NotImplementedError(f"head_dim={self.head_dim}: the sm_100a attention kernel is specialised on 64")
         if self.training and self.dropout > 0.0:
             raise NotImplementedError("attention dropout (training mode) is not supported; call .eval()")
+
+    def _bias_view(self, attn_bias: Tensor | None, B: int, Lq: int, Lkv: int) -> Tensor | None:
+        """``attn_bias`` as SDPA takes it (transformer.py:52: float added to the scores, or bool with True = attend),
+        broadcast to (B, H, Lq, Lkv) without materialising the broadcast dimensions."""
+        if attn_bias is None:
+            return None
+        b = attn_bias
+        if b.dtype == torch.bool:
+            b = torch.zeros(b.shape, device=b.device, dtype=torch.float32).masked_fill_(~b, float("-inf"))
+        b = b.to(torch.float32)
+        if b.dim() > 4:
+            b = b.reshape(-1, *b.shape[-3:])
+        if b.stride(-1) != 1 and b.shape[-1] > 1:
+            b = b.contiguous()
+        return b.expand(B, self.n_heads, Lq, Lkv)
 
     @property
     def scale(self) -> float:
@@ -196,7 +209,7 @@ class MHA(nn.Module):
                 qv = qv.expand(Bk, Lq, inner).contiguous()
                 B = Bk
         att = torch.empty(B, Lq, inner, device=dev, dtype=torch.bfloat16)
-        ops.attention(qv, kv_k, kv_v, att, self.n_heads, self.scale, causal)
+        ops.attention(qv, kv_k, kv_v, att, self.n_heads, self.scale, causal, self._bias_view(attn_bias, B, Lq, kv_k.shape[1]))
         po = self._pack("out", [self.out_proj])
         out = torch.empty(B, Lq, self.out_proj.out_features, device=dev, dtype=torch.bfloat16)
         ops.linear(att.view(B * Lq, inner), po.w, po.bias, out.view(B * Lq, -1))

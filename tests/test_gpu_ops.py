@@ -178,6 +178,34 @@ def test_embed_rows(dtype):
     assert torch.equal(out[ok], want[ok])
 
 
+@pytest.mark.parametrize("shape", ["LL", "HLL", "B1LL", "BHLL", "bool"])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_bias_matches_sdpa(shape, causal):
+    """attn_bias of MHA.forward (transformer.py:41,52) in every broadcast shape SDPA accepts, float and bool, alone
+    and combined with the causal flag; -inf entries mask keys."""
+    import pytorch_models_b200 as pm
+
+    torch.manual_seed(3)
+    B, H, L, d = 2, 2, 200, 128
+    mha = pm.MHA(d).eval().cuda()
+    x = torch.randn(B, L, d, device="cuda")
+    full = torch.randn(B, H, L, L, device="cuda") * 2
+    full[:, :, :, 150:170] = float("-inf")   # a band of masked keys
+    bias = {"LL": full[0, 0], "HLL": full[0], "B1LL": full[:, :1], "BHLL": full,
+            "bool": torch.rand(L, L, device="cuda") > 0.3}[shape]
+    if shape == "bool":
+        bias = bias | torch.eye(L, device="cuda", dtype=torch.bool)  # keep every row attendable
+    with torch.no_grad():
+        got = mha(x, attn_bias=bias, causal=causal)
+        q, k, v = (getattr(mha, n)(x).unflatten(-1, (H, 64)).transpose(1, 2) for n in ("q_proj", "k_proj", "v_proj"))
+        mask = bias if bias.dtype != torch.bool else torch.zeros(L, L, device="cuda").masked_fill(~bias, float("-inf"))
+        if causal:
+            mask = mask + torch.zeros(L, L, device="cuda").masked_fill(
+                ~torch.ones(L, L, device="cuda", dtype=torch.bool).tril(), float("-inf"))
+        want = mha.out_proj(F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).flatten(-2))
+    _close(got, want, 0.03, 0.03)
+
+
 def test_cross_attention_one_query():
     """The MAP-pooling shape (vit.py:41): 1 query row against L keys."""
     from pytorch_models_b200 import ops

@@ -96,7 +96,7 @@ def test_no_cpu_fallback():
 def test_unsupported_arguments_raise_not_implemented():
     x = torch.randn(1, 4, 128)
     mha = pm.MHA(128).eval()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         mha(x, attn_bias=torch.zeros(4, 4))
     with pytest.raises(NotImplementedError):
         pm.MHA(128, head_dim=32).eval()(x)
