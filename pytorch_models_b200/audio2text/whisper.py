@@ -19,9 +19,11 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
+from ..compile import compilable, compilable_module, float_like
 from ..transformer import Decoder, Encoder, TiedLogits, _as_tokens, _Packed, embed_tokens, norm_vectors
 
 
+@compilable_module
 class WhisperEncoder(nn.Module):
     max_seq_len = 3000
 
@@ -87,6 +89,7 @@ class WhisperEncoder(nn.Module):
         ops.linear(a2, pk.w2, pk.b2, tokens, gelu=True, residual=pk.pos[:T2].unsqueeze(0))
         return tokens
 
+    @compilable(lambda self, x, extra: ((x.shape[0], (x.shape[2] - 1) // 2 + 1, self.stem[0].out_channels), float_like(x)))
     def forward(self, x: Tensor) -> Tensor:
         out_dtype = x.dtype if x.dtype in (torch.bfloat16, torch.float32) else torch.float32
         h = self.layers.run(self.embed(x))
@@ -134,6 +137,7 @@ def _load_openai(half: nn.Module, state_dict: dict, prefix: str) -> None:
     take(half.norm, "ln_post" if prefix == "encoder" else "ln")
 
 
+@compilable_module
 class WhisperDecoder(nn.Module):
     """Reference ``WhisperDecoder`` (whisper.py:37-53)."""
 
@@ -147,6 +151,7 @@ class WhisperDecoder(nn.Module):
         self.norm = nn.LayerNorm(d_model)
         self._logits = TiedLogits()
 
+    @compilable(lambda self, x, extra: ((*x.shape, self.token_embs.weight.shape[0]), self.token_embs.weight.dtype))
     def forward(self, x: Tensor, memory: Tensor) -> Tensor:
         """x: (N, L) int64 token ids, memory: (N, Lm, d) encoder output -> (N, L, vocab) logits (whisper.py:46-52)."""
         out_dtype = self.token_embs.weight.dtype
@@ -174,6 +179,7 @@ _OPENAI_SIZES = {
 }
 
 
+@compilable_module
 class Whisper(nn.Module):
     """Reference ``Whisper`` (whisper.py:56-135): ``decoder(targets, encoder(x))``."""
 
@@ -182,6 +188,8 @@ class Whisper(nn.Module):
         self.encoder = WhisperEncoder(n_layers, d_model, n_mels, dropout=dropout)
         self.decoder = WhisperDecoder(vocab_size, n_layers, d_model, dropout=dropout)
 
+    @compilable(lambda self, x, extra: ((*extra.shape, self.decoder.token_embs.weight.shape[0]),
+                                        self.decoder.token_embs.weight.dtype))
     def forward(self, x: Tensor, targets: Tensor) -> Tensor:
         return self.decoder(targets, self.encoder(x))
 
@@ -223,6 +231,7 @@ def mel_filters(n_mels: int, n_fft: int, sample_rate: float) -> Tensor:
     return bank
 
 
+@compilable_module
 class WhisperPreprocessor(nn.Module):
     """Reference ``WhisperPreprocessor`` (whisper.py:138-148): raw 16 kHz audio (N, L) -> normalised log-mel
     (N, n_mels, L // 160). Same buffers as the reference (``window`` non-persistent, ``filters`` persistent); the
@@ -236,6 +245,7 @@ class WhisperPreprocessor(nn.Module):
         self.register_buffer("filters", mel_filters(n_mels, self.n_fft, 16_000))
         self._pf = _Packed()
 
+    @compilable(lambda self, x, extra: ((*x.shape[:-1], self.filters.shape[0], x.shape[-1] // 160), x.dtype))
     def forward(self, x: Tensor) -> Tensor:
         if not x.is_cuda:
             raise RuntimeError("pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from .. import ops
+from ..compile import compilable, compilable_module, float_like
 from ..transformer import MHA, MLP, Encoder, _Packed, norm_vectors, pack_folded
 
 _SIZES = dict(Ti=(12, 192, 3), S=(12, 384, 6), M=(12, 512, 8), B=(12, 768, 12), L=(24, 1024, 16), H=(32, 1280, 16))
@@ -69,6 +70,7 @@ class MHAPooling(nn.Module):
         return out
 
 
+@compilable_module
 class ViT(nn.Module):
     norm_eps = 1e-6
 
@@ -146,6 +148,7 @@ class ViT(nn.Module):
             ops.cls_rows(pk.cls, tokens)
         return tokens
 
+    @compilable(lambda self, x, extra: ((x.shape[0], self.norm.normalized_shape[0]), float_like(x)))
     def forward(self, imgs: Tensor) -> Tensor:
         out_dtype = imgs.dtype if imgs.dtype in (torch.bfloat16, torch.float32) else torch.float32
         if imgs.shape[0] == 0:

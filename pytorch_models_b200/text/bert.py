@@ -12,9 +12,11 @@ import torch
 from torch import Tensor, nn
 
 from .. import ops
+from ..compile import compilable, compilable_module
 from ..transformer import Encoder, embed_tokens, norm_vectors
 
 
+@compilable_module
 class BERT(nn.Module):
     def __init__(
         self,
@@ -32,6 +34,7 @@ class BERT(nn.Module):
         self.norm = nn.LayerNorm(d_model, norm_eps)
         self.layers = Encoder(n_layers, d_model, dropout=dropout, pre_norm=False, norm_eps=norm_eps)
 
+    @compilable(lambda self, x, extra: ((*x.shape, self.token_embs.weight.shape[1]), self.token_embs.weight.dtype))
     def forward(self, x: Tensor) -> Tensor:
         out_dtype = self.token_embs.weight.dtype
         emb3 = embed_tokens(x, self.token_embs, self.pos_embs)

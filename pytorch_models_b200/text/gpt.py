@@ -5,9 +5,11 @@ from __future__ import annotations
 import torch
 from torch import Tensor, nn
 
+from ..compile import compilable, compilable_module
 from ..transformer import Decoder, TiedLogits, embed_tokens
 
 
+@compilable_module
 class GPT(nn.Module):
     vocab_size = 40478
     max_seq_len: int = 512
@@ -19,6 +21,7 @@ class GPT(nn.Module):
         self.layers = Decoder(n_layers, d_model, dropout=dropout, pre_norm=False, act="approximate_gelu")
         self._logits = TiedLogits()
 
+    @compilable(lambda self, x, extra: ((*x.shape, self.token_embs.weight.shape[0]), self.token_embs.weight.dtype))
     def forward(self, x: Tensor) -> Tensor:
         """(*, L) int64 token ids -> (*, L, vocab) logits in the parameters' dtype (gpt.py:24-29)."""
         out_dtype = self.token_embs.weight.dtype

@@ -10,9 +10,11 @@ from __future__ import annotations
 import torch
 from torch import Tensor, nn
 
+from ..compile import compilable, compilable_module
 from ..transformer import Decoder, TiedLogits, embed_tokens
 
 
+@compilable_module
 class GPT2(nn.Module):
     vocab_size = 50257
     max_seq_len: int = 1024
@@ -25,6 +27,7 @@ class GPT2(nn.Module):
         self.norm = nn.LayerNorm(d_model)
         self._logits = TiedLogits()
 
+    @compilable(lambda self, x, extra: ((*x.shape, self.token_embs.weight.shape[0]), self.token_embs.weight.dtype))
     def forward(self, x: Tensor) -> Tensor:
         """(*, L) int64 token ids -> (*, L, vocab) logits in the parameters' dtype (gpt2.py:21-27)."""
         out_dtype = self.token_embs.weight.dtype

@@ -29,6 +29,7 @@ import torch
 from torch import Tensor, nn
 
 from . import ops
+from .compile import compilable, compilable_module
 
 _SUPPORTED_HEAD_DIM = 64
 _MAX_STAT_PARTS = 12  # libb200enc combines at most 12 partial statistics per row (d <= 1536)
@@ -468,6 +469,7 @@ def norm_vectors(norm: nn.LayerNorm) -> tuple[Tensor, Tensor]:
     return hit[1]
 
 
+@compilable_module
 class Encoder(nn.Sequential):
     """Reference ``Encoder`` (transformer.py:133-149): an ``nn.Sequential`` of ``EncoderLayer`` — iteration, ``len``
     and indexing behave the same; ``forward`` additionally shares one workspace across the layers."""
@@ -494,6 +496,7 @@ class Encoder(nn.Sequential):
         """bf16 contiguous (B, L, d) -> new tensor of the same shape; x3 is left untouched."""
         return _run_stack(list(self), x3, None)
 
+    @compilable(lambda self, x, extra: (x.shape, x.dtype))
     def forward(self, x: Tensor) -> Tensor:
         x3, meta = _as_tokens(x, self.d_model)
         return _restore(self.run(x3), meta)
@@ -518,6 +521,7 @@ def _run_stack(layers: list, x3: Tensor, memory3: Tensor | None, final_stats: bo
     return (cur, stats) if final_stats else cur
 
 
+@compilable_module
 class Decoder(nn.ModuleList):
     """Reference ``Decoder`` (transformer.py:152-176): an ``nn.ModuleList`` of ``DecoderLayer`` called as
     ``decoder(x, memory)``; ``forward`` additionally shares one workspace across the layers."""
@@ -548,6 +552,7 @@ class Decoder(nn.ModuleList):
         ``final_stats``: also return the output rows' partial LayerNorm statistics (see `_run_stack`)."""
         return _run_stack(list(self), x3, memory3, final_stats)
 
+    @compilable(lambda self, x, extra: (x.shape, x.dtype))
     def forward(self, x: Tensor, memory: Tensor | None = None) -> Tensor:
         x3, meta = _as_tokens(x, self.d_model)
         m3 = None

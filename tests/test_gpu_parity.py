@@ -254,3 +254,28 @@ def test_whisper_audio_to_encoder_end_to_end():
         got = enc.cuda()(pre.cuda()(audio.cuda())).float().cpu()
     max_abs, min_cos = error_stats(got.numpy(), want.numpy())
     assert max_abs <= MAX_ABS_12 and min_cos >= MIN_COS, (max_abs, min_cos)
+
+
+def test_torch_compile_fullgraph_matches_eager(golden):
+    """Reference guarantee (README.md:7, tests/*/test_*.py `torch.compile(m, fullgraph=True)`): the compiled model is
+    one b200enc::module_forward node and returns exactly what the eager call returns."""
+    with torch.no_grad():
+        g = golden("vit_cls")
+        m = build_model(g).cuda()
+        x = torch.from_numpy(np.array(g.input)).cuda()
+        want = m(x)
+        for backend in ("aot_eager", "inductor"):
+            torch._dynamo.reset()
+            got = torch.compile(m, fullgraph=True, backend=backend)(x)
+            assert torch.equal(got, want), backend
+        torch._dynamo.reset()
+        g = golden("whisper_full")
+        w = build_model(g).cuda()
+        audio = torch.from_numpy(np.array(g.input)).cuda()
+        targets = torch.from_numpy(np.array(g.extra["targets"])).cuda()
+        assert torch.equal(torch.compile(w, fullgraph=True, backend="aot_eager")(audio, targets), w(audio, targets))
+        torch._dynamo.reset()
+        g = golden("gpt2")
+        lm = build_model(g).cuda().bfloat16()
+        ids = torch.from_numpy(np.array(g.input)).cuda()
+        assert torch.equal(torch.compile(lm, fullgraph=True, backend="aot_eager")(ids), lm(ids))

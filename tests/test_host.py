@@ -224,3 +224,39 @@ def test_whisper_preprocessor_mirrors_reference_buffers(golden):
     assert pm.WhisperPreprocessor().filters.shape == (80, 201)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1600))
+
+
+def test_torch_compile_fullgraph_traces_to_one_operator():
+    """`torch.compile(m, fullgraph=True)` (reference tests: test_vit.py:14-18, test_gpt2.py:22, test_bert.py:22) must
+    trace without a graph break: the whole forward is one b200enc::module_forward node. On this CPU-only box the node
+    then raises the package's own 'no CPU fallback' error — a Dynamo `Unsupported` would mean a graph break."""
+    import copy
+
+    from pytorch_models_b200 import compile as pmc
+
+    with torch.no_grad():
+        for make, args in (
+            (lambda: pm.ViT.from_google("Ti/16"), (torch.randn(1, 3, 224, 224),)),
+            (lambda: pm.BERT(100, 1, 64), (torch.randint(0, 100, (1, 8)),)),
+            (lambda: pm.GPT2(1, 64), (torch.randint(0, 100, (1, 8)),)),
+            (lambda: pm.WhisperEncoder(1, 64), (torch.randn(1, 80, 16),)),
+            (lambda: pm.Whisper(100, 1, 64), (torch.randn(1, 80, 16), torch.randint(0, 100, (1, 4)))),
+            (lambda: pm.Encoder(1, 64), (torch.randn(1, 4, 64),)),
+            (lambda: pm.Decoder(1, 64, cross_attn=True), (torch.randn(1, 4, 64), torch.randn(1, 6, 64))),
+        ):
+            m = make().eval()
+            assert isinstance(m._b200_module_id, int) and "_b200_module_id" not in m.state_dict()
+            compiled = torch.compile(m, fullgraph=True, backend="eager")
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                compiled(*args)
+    # the fake implementation describes the output without running anything
+    m = pm.GPT2(1, 64)
+    shape, dtype = type(m).forward._out_meta(m, torch.zeros(2, 5, dtype=torch.long), None)
+    assert tuple(shape) == (2, 5, 50257) and dtype == torch.float32
+    v = pm.ViT.from_google("Ti/16")
+    assert type(v).forward._out_meta(v, torch.zeros(3, 3, 224, 224), None) == ((3, 192), torch.float32)
+    # every instance has its own id; a deep copy has to be registered by hand before it is compiled
+    a, b = pm.Encoder(1, 64), pm.Encoder(1, 64)
+    assert a._b200_module_id != b._b200_module_id
+    c = copy.deepcopy(a)
+    assert c._b200_module_id == a._b200_module_id and pmc.register(c) != a._b200_module_id
