@@ -74,6 +74,28 @@ struct AttnParams {
 // valid columns; `masked` (warp-uniform): the block has a partial last chunk or holds the causal diagonal — columns
 // >= lim are set to -inf before the maximum, after which the exponential pass needs no predicates.
 // (One copy of this code on purpose: two inlined specialisations made ptxas spill the 128-register row.)
+// Every ATT_POLY_EVERY-th pair of scores takes its exponentials from exp2_poly2 instead of MUFU.EX2 (0 = never).
+// Same-box A/B at 25 %: L=1500 0.176 -> 0.169 ms, L=576 0.110 -> 0.106 ms, L=197 0.0555 -> 0.0545 ms; 50 % is slower
+// than none (the FMA pipe and the issue slots become the limit), 12-33 % are within noise of each other.
+#ifndef ATT_POLY_EVERY
+#define ATT_POLY_EVERY 4
+#endif
+// 2^x for x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], max relative error
+// 7.7e-5, far below the bf16 rounding of P): takes a share of the exponentials off the MUFU pipe.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x = make_float2(fmaxf(x.x, -126.0f), fmaxf(x.y, -126.0f));
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23: the sum's low mantissa bits hold round(x)
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.05508868396282196f, 0.05508868396282196f),
+                        make_float2(0.24260404706001282f, 0.24260404706001282f));
+  q = __ffma2_rn(q, f, make_float2(0.6932762265205383f, 0.6932762265205383f));
+  q = __ffma2_rn(q, f, make_float2(0.9999289512634277f, 0.9999289512634277f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+
 // kBias: x = s * c + bias * log2(e) is formed right after the load (bias_row points at this row's bias for the
 // block's first column, n_cols = valid columns of the block) and the rest runs with c = 1.
 template <bool kBias>
@@ -137,7 +159,12 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
       for (int i = 0; i < 16; ++i) {
         const float2 e = __ffma2_rn(make_float2(__uint_as_float(v[ch][2 * i]), __uint_as_float(v[ch][2 * i + 1])), c2,
                                     nmc2);
+#if ATT_POLY_EVERY > 0
+        const float2 pr = (i % ATT_POLY_EVERY) == ATT_POLY_EVERY - 1 ? exp2_poly2(e)
+                                                                     : make_float2(fast_exp2(e.x), fast_exp2(e.y));
+#else
         const float2 pr = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+#endif
         if (i & 1) sum1 = __fadd2_rn(sum1, pr); else sum0 = __fadd2_rn(sum0, pr);
         pk[i] = pack_bf16x2(pr.x, pr.y);
       }
