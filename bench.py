@@ -21,6 +21,7 @@ import time
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+RESULT_OUT = sys.stdout  # replaced in __main__ by a duplicate of the original stdout
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -179,7 +180,7 @@ def run_reference_arm(args, cfg: dict) -> None:
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -384,10 +385,15 @@ def main() -> None:
             "model_tflops": value * fl / 1e12, "model_frac_of_burst_peak": value * fl / 1e12 / world / peaks["burst"],
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: everything else that might write to file descriptor 1 (NCCL's version
+    # banner, library printf) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     main()
