@@ -206,6 +206,28 @@ def test_attention_bias_matches_sdpa(shape, causal):
     _close(got, want, 0.03, 0.03)
 
 
+@pytest.mark.parametrize("gain", [0.05, 4.0, 12.0])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_extreme_score_ranges(gain, causal):
+    """Nearly uniform and extremely peaked softmax rows (|score| up to a few hundred): the lazily updated maximum
+    (rescale only beyond 2^8 of head-room), the accumulator rescale in TMEM and the polynomial exp2 must hold."""
+    from pytorch_models_b200 import ops
+
+    B, H, L = 2, 2, 700
+    g = torch.Generator(device="cuda").manual_seed(int(gain * 100) + causal)
+    qkv = torch.randn(B, L, 3 * H * 64, device="cuda", generator=g)
+    qkv[..., : 2 * H * 64] *= gain                      # q and k: scores ~ gain^2 * 8 * N(0,1)
+    qkv[:, 500:, H * 64: 2 * H * 64] *= 3.0             # late keys dominate: forces rescales in later blocks
+    qkv = qkv.bfloat16()
+    out = torch.empty(B, L, H * 64, device="cuda", dtype=torch.bfloat16)
+    q, k, v = qkv[:, :, : H * 64], qkv[:, :, H * 64: 2 * H * 64], qkv[:, :, 2 * H * 64:]
+    ops.attention(q, k, v, out, H, 0.125, causal=causal)
+    heads = lambda t: t.double().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(k), heads(v), is_causal=causal).transpose(1, 2).flatten(-2)
+    assert bool(torch.isfinite(out).all())
+    _close(out, want.float(), 0.03, 0.03)
+
+
 def test_cross_attention_one_query():
     """The MAP-pooling shape (vit.py:41): 1 query row against L keys."""
     from pytorch_models_b200 import ops
