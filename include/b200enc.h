@@ -73,6 +73,9 @@ typedef struct b200enc_linear_args {
   float* stats_out;            /* fp32 pairs [(batches*M)][ceil(N/128)] or NULL */
   int batches, M, N, K;
   int flags;
+  int stats_rows_per_batch;    /* 0 = M. Otherwise row (b, m) of stats_out lives at b*stats_rows_per_batch +            */
+  int stats_row_offset;        /* stats_row_offset + m: lets the patch-embedding GEMM, which writes tokens 1.. of every */
+                               /* image, put its statistics where the first encoder layer looks for them               */
 } b200enc_linear_args;
 
 int b200enc_linear(const b200enc_linear_args* args, void* stream);

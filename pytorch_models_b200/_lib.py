@@ -37,6 +37,7 @@ class LinearArgs(ctypes.Structure):
         ("stats_out", c_void_p),
         ("batches", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
         ("flags", c_int),
+        ("stats_rows_per_batch", c_int), ("stats_row_offset", c_int),
     ]
 
 

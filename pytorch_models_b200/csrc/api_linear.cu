@@ -131,6 +131,11 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   p.stat_parts = a->rowstats_parts;
   p.ln_eps = a->ln_eps;
   p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  p.stats_rows = a->stats_rows_per_batch > 0 ? a->stats_rows_per_batch : M;
+  p.stats_off = a->stats_row_offset;
+  B200_CHECK_ARG(a->stats_row_offset >= 0 && p.stats_rows >= M + a->stats_row_offset,
+                 "b200enc_linear: stats_rows_per_batch=%d cannot hold M=%d rows at offset %d", p.stats_rows, M,
+                 a->stats_row_offset);
   p.res = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.res_batch_stride = a->res_batch_stride;
   p.ldr = a->ldr;

@@ -60,7 +60,9 @@ struct GemmParams {
                              // [batches*M][stat_parts] partial (mean_t, M2_t) over 128-column slices of the row
   int stat_parts;
   float ln_eps;
-  float2* stats_out;         // kStats: [batches*M][ceil(N/128)] partial (mean_t, M2_t) of the OUTPUT rows
+  float2* stats_out;         // kStats: partial (mean_t, M2_t) of the OUTPUT rows, row (b, m) at
+                             // [b * stats_rows + stats_off + m][ceil(N/128)]  (stats_rows = M, stats_off = 0 by default)
+  int stats_rows, stats_off;
   const __nv_bfloat16* res;  // residual / positional table, nullptr if unused
   long long res_batch_stride;  // elements; 0 => same table for every batch (positional embedding)
   int ldr;                     // residual row stride (elements)
@@ -427,7 +429,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float s1 = st_s1.x + st_s1.y, s2 = st_s2.x + st_s2.y;
         const float mean_t = st_shift + s1 / nt;
         const float m2_t = fmaxf(s2 - s1 * s1 / nt, 0.0f);
-        p.stats_out[((long long)b * p.M + row) * n_slices + nh / GEMM_STAT_SLICE] = make_float2(mean_t, m2_t);
+        p.stats_out[((long long)b * p.stats_rows + p.stats_off + row) * n_slices + nh / GEMM_STAT_SLICE] =
+            make_float2(mean_t, m2_t);
       }
       if (!released) {  // warp owned no valid columns in this tile (N tail) or the epilogue body was skipped
         tc_fence_before();

@@ -18,7 +18,7 @@ from torch import Tensor, nn
 
 from .. import ops
 from ..compile import compilable, compilable_module, float_like
-from ..transformer import MHA, MLP, Encoder, _Packed, norm_vectors, pack_folded
+from ..transformer import partial_stats_of, MHA, MLP, Encoder, _Packed, norm_vectors, pack_folded
 
 _SIZES = dict(Ti=(12, 192, 3), S=(12, 384, 6), M=(12, 512, 8), B=(12, 768, 12), L=(24, 1024, 16), H=(32, 1280, 16))
 
@@ -120,13 +120,16 @@ class ViT(nn.Module):
                 w=w, bias=bias, kpad=kpad,
                 pe=self.pe.detach().to(torch.bfloat16).contiguous(),
                 cls=None if cls is None else cls.detach().to(torch.bfloat16).contiguous(),
+                cls_stats=None if cls is None else partial_stats_of(cls),
             )
 
         return self._pembed.get((conv.weight, conv.bias, self.pe, cls), build)
 
     # -- forward -------------------------------------------------------------------------------
-    def embed(self, imgs: Tensor) -> Tensor:
-        """(N, 3, H, W) -> contiguous bf16 tokens (N, L, d) with the class token (if any) at position 0."""
+    def embed(self, imgs: Tensor, with_stats: bool = False):
+        """(N, 3, H, W) -> contiguous bf16 tokens (N, L, d) with the class token (if any) at position 0.
+        ``with_stats``: also return the rows' partial LayerNorm statistics (N*L, ceil(d/128), 2), written by the
+        patch-embedding GEMM's epilogue (and, for the class token, copied from a cached vector), or None."""
         if not imgs.is_cuda:
             raise RuntimeError("pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")
         if imgs.dtype not in (torch.bfloat16, torch.float32):
@@ -143,9 +146,17 @@ class ViT(nn.Module):
         rows = torch.empty(N, P, pk.kpad, device=imgs.device, dtype=torch.bfloat16)
         tokens = torch.empty(N, P + off, d, device=imgs.device, dtype=torch.bfloat16)
         ops.patch_rows(imgs, p, pk.kpad, rows)
-        ops.linear(rows, pk.w, pk.bias, tokens[:, off:, :], residual=pk.pe)
+        stats = None
+        if with_stats and self.layers.wants_stats():
+            stats = torch.empty(N, P + off, (d + 127) // 128, 2, device=imgs.device, dtype=torch.float32)
+        ops.linear(rows, pk.w, pk.bias, tokens[:, off:, :], residual=pk.pe, stats_out=stats, stats_rows=P + off,
+                   stats_row_offset=off)
         if off:
             ops.cls_rows(pk.cls, tokens)
+            if stats is not None:
+                ops.broadcast_row(pk.cls_stats, stats)
+        if with_stats:
+            return tokens, (None if stats is None else stats.view(N * (P + off), -1, 2))
         return tokens
 
     @compilable(lambda self, x, extra: ((x.shape[0], self.norm.normalized_shape[0]), float_like(x)))
@@ -153,7 +164,8 @@ class ViT(nn.Module):
         out_dtype = imgs.dtype if imgs.dtype in (torch.bfloat16, torch.float32) else torch.float32
         if imgs.shape[0] == 0:
             return torch.empty(0, self.norm.normalized_shape[0], device=imgs.device, dtype=out_dtype)
-        x = self.layers.run(self.embed(imgs))
+        tokens, stats = self.embed(imgs, with_stats=True)
+        x = self.layers.run(tokens, stats)
         N, L, d = x.shape
         gamma, beta = norm_vectors(self.norm)
         if isinstance(self.pooler, ClassTokenPooling):

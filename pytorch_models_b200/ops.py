@@ -75,6 +75,8 @@ def linear(
     direct_store: bool = False,
     ln_eps: float = 0.0,
     stats_out: Tensor | None = None,
+    stats_rows: int = 0,
+    stats_row_offset: int = 0,
 ) -> Tensor:
     """out[b, m, :] = epilogue(x[b, m, :] @ w.T); x, out, residual are (batches, M, *) views with unit inner stride.
 
@@ -83,7 +85,8 @@ def linear(
     A residual with a leading dimension of 1 is broadcast over the batch (positional embedding).
     ``rowstats`` is either (batches*M, 2) = (mean, rstd) from `row_stats`, or (batches*M, parts, 2) partial
     (mean, M2) per 128 input columns as written through ``stats_out`` by the linear that produced ``x``
-    (then ``ln_eps`` is required). ``stats_out``: (batches*M, ceil(N/128), 2) fp32, needs a residual epilogue.
+    (then ``ln_eps`` is required). ``stats_out``: (batches*M, ceil(N/128), 2) fp32, needs a residual epilogue; with
+    ``stats_rows`` > 0 it is (batches*stats_rows, ceil(N/128), 2) and row (b, m) goes to b*stats_rows + stats_row_offset + m.
     """
     _need_cuda(x, w, bias, out, colsum, rowstats, residual)
     _need(x, torch.bfloat16, "x"), _need(w, torch.bfloat16, "w"), _need(out, torch.bfloat16, "out")
@@ -110,8 +113,10 @@ def linear(
         if not rowstats.is_contiguous() or rowstats.numel() % (2 * batches * M) != 0:
             raise ValueError("rowstats must be a contiguous (batches*M, 2) or (batches*M, parts, 2) tensor")
         parts = 0 if rowstats.dim() == 2 else rowstats.shape[1]
-    if stats_out is not None and (not stats_out.is_contiguous() or stats_out.numel() != 2 * batches * M * ((N + 127) // 128)):
-        raise ValueError("stats_out must be a contiguous (batches*M, ceil(N/128), 2) tensor")
+    srows = stats_rows if stats_rows > 0 else M
+    if stats_out is not None and (not stats_out.is_contiguous() or srows < M + stats_row_offset or stats_row_offset < 0
+                                  or stats_out.numel() != 2 * batches * srows * ((N + 127) // 128)):
+        raise ValueError("stats_out must be a contiguous (batches*rows, ceil(N/128), 2) tensor that holds every row")
     acts = {False: 0, True: _lib.LINEAR_GELU, "tanh": _lib.LINEAR_GELU_TANH, "relu": _lib.LINEAR_RELU,
             "silu": _lib.LINEAR_SILU}
     if isinstance(gelu, (bool, str)) and gelu in acts:
@@ -122,7 +127,7 @@ def linear(
     args = _lib.LinearArgs(
         x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum),
         _ptr(rowstats), parts, float(ln_eps), _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1),
-        _ptr(stats_out), batches, M, N, K, flags,
+        _ptr(stats_out), batches, M, N, K, flags, int(stats_rows), int(stats_row_offset),
     )
     _call(
         "b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=colsum is not None, gelu=gelu, res=residual is not None),
@@ -242,6 +247,20 @@ def cls_rows(cls: Tensor, tokens: Tensor) -> Tensor:
         cls.data_ptr(), B, d, tokens.data_ptr(), tokens.stride(0), _stream()
     )
     return tokens
+
+
+def broadcast_row(row: Tensor, dst: Tensor) -> Tensor:
+    """dst[b, 0, ...] = row for every b: dst (B, rows, *) fp32 / bf16 contiguous, row = one (*)-shaped slice. The same
+    kernel as `cls_rows` (a strided broadcast of raw 16-bit units), used for the class token's LayerNorm statistics."""
+    _need_cuda(row, dst)
+    if row.dtype != dst.dtype or not (row.is_contiguous() and dst.is_contiguous()) or dst[0, 0].numel() != row.numel():
+        raise ValueError("broadcast_row expects a contiguous row that matches dst[b, 0]")
+    units = row.element_size() // 2
+    _call(
+        "b200enc_cls_rows", None,
+        row.data_ptr(), dst.shape[0], row.numel() * units, dst.data_ptr(), dst.stride(0) * units, _stream()
+    )
+    return dst
 
 
 def time_rows(x: Tensor, rows: Tensor) -> Tensor:

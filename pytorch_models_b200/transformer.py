@@ -5,7 +5,8 @@ Same class names, constructor signatures, attribute names and ``state_dict`` key
 into ``layer.sa.q_proj.weight`` etc.) keep working. The arithmetic does not run in PyTorch: ``forward`` sequences
 hand-written sm_100a kernels from ``libb200enc.so``:
 
-    pre-norm layer (transformer.py:125-126), 5 launches (+1 row_stats for the first layer of a stack)
+    pre-norm layer (transformer.py:125-126), 5 launches (+1 row_stats for the first layer of a stack whose input
+    did not come with statistics; ViT's patch-embedding GEMM provides them)
         linear [3·inner, d], LayerNorm folded -> fused q|k|v                  (transformer.py:87,47-49)
         attention                             -> softmax(q kᵀ/√64) v          (transformer.py:52)
         linear out_proj + bias + residual     -> x1 (+ partial LN statistics) (transformer.py:53,125)
@@ -492,9 +493,15 @@ class Encoder(nn.Sequential):
             self.append(EncoderLayer(d_model, n_heads, head_dim, bias, mlp_ratio, dropout, act, pre_norm, norm_eps))
         self.d_model = d_model
 
-    def run(self, x3: Tensor) -> Tensor:
-        """bf16 contiguous (B, L, d) -> new tensor of the same shape; x3 is left untouched."""
-        return _run_stack(list(self), x3, None)
+    def run(self, x3: Tensor, stats: Tensor | None = None) -> Tensor:
+        """bf16 contiguous (B, L, d) -> new tensor of the same shape; x3 is left untouched. ``stats``: partial
+        LayerNorm statistics of x3's rows, (B*L, ceil(d/128), 2), if the kernel that produced x3 emitted them."""
+        return _run_stack(list(self), x3, None, stats0=stats)
+
+    def wants_stats(self) -> bool:
+        """True if the first layer can consume partial statistics written by the producer of its input."""
+        layers = list(self)
+        return bool(layers) and layers[0].pre_norm and (self.d_model + 127) // 128 <= _MAX_STAT_PARTS
 
     @compilable(lambda self, x, extra: (x.shape, x.dtype))
     def forward(self, x: Tensor) -> Tensor:
@@ -502,18 +509,32 @@ class Encoder(nn.Sequential):
         return _restore(self.run(x3), meta)
 
 
-def _run_stack(layers: list, x3: Tensor, memory3: Tensor | None, final_stats: bool = False):
+def partial_stats_of(row: Tensor) -> Tensor:
+    """(parts, 2) fp32 per-128-column (mean, M2) of one stored bf16 row — what the GEMM epilogue writes for the rows it
+    produces; used for rows that no GEMM produces (the class token)."""
+    v = row.detach().to(torch.bfloat16).float().flatten()
+    out = []
+    for c0 in range(0, v.numel(), 128):
+        sl = v[c0:c0 + 128]
+        mean = sl.mean()
+        out.append(torch.stack([mean, ((sl - mean) ** 2).sum()]))
+    return torch.stack(out).contiguous()
+
+
+def _run_stack(layers: list, x3: Tensor, memory3: Tensor | None, final_stats: bool = False,
+               stats0: Tensor | None = None):
     """Run a list of layers over bf16 contiguous (B, L, d) tokens with one shared workspace and two ping-pong output
     buffers; the LayerNorm statistics travel from each layer's last GEMM to the next layer's first.
 
     With ``final_stats`` returns ``(tokens, stats)`` where stats are the partial LayerNorm statistics of the output
-    rows (None when the stack cannot produce them) for a LayerNorm folded into whatever consumes the tokens."""
+    rows (None when the stack cannot produce them) for a LayerNorm folded into whatever consumes the tokens.
+    ``stats0``: partial statistics of x3's rows if its producer wrote them (saves the first layer's row_stats pass)."""
     if not layers or x3.numel() == 0:
         return (x3.clone(), None) if final_stats else x3.clone()
     B, L, _ = x3.shape
     ws = layers[0].workspace(B, L, x3.device, 0 if memory3 is None else memory3.shape[1])
     bufs = [torch.empty_like(x3), torch.empty_like(x3) if len(layers) > 1 else None]
-    cur, stats = x3, None
+    cur, stats = x3, stats0
     for i, layer in enumerate(layers):
         want = final_stats or i + 1 < len(layers)
         stats = layer.run(cur, bufs[i % 2], ws, stats_in=stats, want_stats=want, memory3=memory3)
