@@ -59,8 +59,9 @@ class WhisperEncoder(nn.Module):
 
         return self._pstem.get((c1.weight, c1.bias, c2.weight, c2.bias, self.pos_embs), build)
 
-    def embed(self, x: Tensor) -> Tensor:
-        """(N, n_mels, T) log-mel -> contiguous bf16 tokens (N, ceil(T/2), d) incl. positional embedding."""
+    def embed(self, x: Tensor, with_stats: bool = False):
+        """(N, n_mels, T) log-mel -> contiguous bf16 tokens (N, ceil(T/2), d) incl. positional embedding.
+        ``with_stats``: also return the rows' partial LayerNorm statistics from the second conv GEMM's epilogue."""
         if not x.is_cuda:
             raise RuntimeError("pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback")
         if x.dtype not in (torch.bfloat16, torch.float32):
@@ -86,13 +87,17 @@ class WhisperEncoder(nn.Module):
         # conv2 (stride 2): output step t reads h1 rows[2t : 2t+3]  (= time steps 2t-1, 2t, 2t+1)
         a2 = h1.as_strided((N, T2, 3 * d), ((T + 3) * d, 2 * d, 1))
         tokens = torch.empty(N, T2, d, device=dev, dtype=torch.bfloat16)
-        ops.linear(a2, pk.w2, pk.b2, tokens, gelu=True, residual=pk.pos[:T2].unsqueeze(0))
-        return tokens
+        stats = None
+        if with_stats and self.layers.wants_stats():
+            stats = torch.empty(N * T2, (d + 127) // 128, 2, device=dev, dtype=torch.float32)
+        ops.linear(a2, pk.w2, pk.b2, tokens, gelu=True, residual=pk.pos[:T2].unsqueeze(0), stats_out=stats)
+        return (tokens, stats) if with_stats else tokens
 
     @compilable(lambda self, x, extra: ((x.shape[0], (x.shape[2] - 1) // 2 + 1, self.stem[0].out_channels), float_like(x)))
     def forward(self, x: Tensor) -> Tensor:
         out_dtype = x.dtype if x.dtype in (torch.bfloat16, torch.float32) else torch.float32
-        h = self.layers.run(self.embed(x))
+        tokens, stats = self.embed(x, with_stats=True)
+        h = self.layers.run(tokens, stats)
         N, L, d = h.shape
         gamma, beta = norm_vectors(self.norm)
         out = torch.empty_like(h)
