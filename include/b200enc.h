@@ -7,7 +7,8 @@
  * weights are bf16 row-major, vectors and statistics fp32. Every call enqueues on `stream` (a cudaStream_t) and
  * returns without synchronising; nothing is allocated or freed by the library.
  *
- * Return value: 0 = ok; < 0 = argument / shape / alignment error; > 0 = cudaError_t or CUresult.
+ * Return value: 0 = ok; < 0 = argument / shape / alignment error (-3: an earlier kernel gave up on a barrier wait, see
+ * b200enc_async_status); > 0 = cudaError_t or CUresult.
  * b200enc_last_error() returns a thread-local description of the last non-zero return.
  */
 #ifndef B200ENC_H_
@@ -21,6 +22,18 @@ extern "C" {
 
 int b200enc_version(void);
 const char* b200enc_last_error(void);
+
+/*
+ * Device-side health. The tcgen05 kernels synchronise their warps through on-chip barriers; every such wait is
+ * bounded (4 s). A wait that runs out stores a non-zero code into a process-wide status word (mapped host memory),
+ * after which the kernel drains without hanging the GPU and every later entry point returns -3 instead of enqueueing
+ * work whose inputs are invalid. Kernels never printf, trap or abort (reference convention: Python exceptions only).
+ * Returns the status word (0 = healthy); clear != 0 also resets it.
+ */
+unsigned int b200enc_async_status(int clear);
+
+/* Tensor maps (CUtensorMap) are encoded once per distinct (pointer, shape, strides, box) and cached; counters for tests. */
+void b200enc_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* flags for b200enc_linear */
 #define B200ENC_LINEAR_GELU 1          /* exact (erf) GELU after bias: nn.GELU(), transformer.py:61 */

@@ -44,6 +44,8 @@ class LinearArgs(ctypes.Structure):
 _SIGNATURES = {
     "b200enc_version": (c_int, []),
     "b200enc_last_error": (ctypes.c_char_p, []),
+    "b200enc_async_status": (ctypes.c_uint, [c_int]),
+    "b200enc_tensor_map_cache_stats": (None, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "b200enc_linear": (c_int, [ctypes.POINTER(LinearArgs), c_void_p]),
     "b200enc_attention": (
         c_int,

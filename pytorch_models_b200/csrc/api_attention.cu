@@ -1,6 +1,10 @@
 // C-ABI entry point for the attention core (see include/b200enc.h).
 #include "../../include/b200enc.h"
+#ifdef ATT_V6
+#include "attention_v6.cuh"
+#else
 #include "attention.cuh"
+#endif
 #include "host_util.h"
 
 using namespace b200;
@@ -16,10 +20,10 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
                      const AttnParams& p, cudaStream_t s) {
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (p.bias != nullptr) {
-    B200_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<true>), ATT_SMEM_BYTES)) return rc;
     attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
   } else {
-    B200_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<false>), ATT_SMEM_BYTES)) return rc;
     attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
   }
   B200_CUDA(cudaGetLastError());
@@ -31,6 +35,7 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
                           long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
                           int H, int Lq, int Lkv, int head_dim, float scale, int flags, const float* bias,
                           long long bias_b_stride, long long bias_h_stride, long long bias_row_stride, void* stream) {
+  if (int rc0 = check_abort("b200enc_attention")) return rc0;
   B200_CHECK_ARG(q && k && v && out, "b200enc_attention: null tensor pointer");
   B200_CHECK_ARG(head_dim == ATT_HD, "b200enc_attention: head_dim=%d is not supported (only 64)", head_dim);
   B200_CHECK_ARG(B >= 1 && H >= 1 && Lq >= 1 && Lkv >= 1, "b200enc_attention: bad shape B=%d H=%d Lq=%d Lkv=%d", B, H,
@@ -65,6 +70,7 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
   p.bias_b_stride = bias_b_stride;
   p.bias_h_stride = bias_h_stride;
   p.bias_row_stride = bias_row_stride;
+  p.abort_word = abort_word();
 #ifdef ATT_TRACE
   p.trace = g_attention_trace;
 #else

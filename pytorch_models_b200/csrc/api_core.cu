@@ -4,3 +4,9 @@
 
 extern "C" int b200enc_version(void) { return B200ENC_VERSION; }
 extern "C" const char* b200enc_last_error(void) { return b200::last_error_buf(); }
+extern "C" unsigned int b200enc_async_status(int clear) { return b200::read_abort_word(clear != 0); }
+extern "C" void b200enc_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  const b200::TmapCacheStats s = b200::tmap_cache_stats();
+  if (hits) *hits = s.hits;
+  if (misses) *misses = s.misses;
+}

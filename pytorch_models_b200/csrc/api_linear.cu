@@ -11,8 +11,8 @@ template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats>;
-  constexpr int kSmem = GemmSmem<kCtas>::kBytes;
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  constexpr int kSmem = GemmSmem<kCtas, kRes>::kBytes;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), kSmem)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -68,6 +68,7 @@ int dispatch_epilogue(int sel, bool tma, bool stats, const CUtensorMap& ta, cons
 
 extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   B200_CHECK_ARG(a != nullptr, "b200enc_linear: null argument struct");
+  if (int rc = check_abort("b200enc_linear")) return rc;
   const int batches = a->batches, M = a->M, N = a->N, K = a->K;
   B200_CHECK_ARG(a->x && a->w && a->out, "b200enc_linear: null tensor pointer");
   B200_CHECK_ARG(batches >= 1 && M >= 1 && N >= 1 && K >= 1, "b200enc_linear: bad shape batches=%d M=%d N=%d K=%d",
@@ -143,6 +144,7 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   p.out_batch_stride = a->out_batch_stride;
   p.ldo = a->ldo;
   p.debug = (a->flags >> 16) & 3;
+  p.abort_word = abort_word();
 
   const long long total = (long long)p.tiles_m * p.tiles_n * batches;
   const int slots = sm_count() / ctas;  // CTAs (or CTA pairs) resident at once: the kernel is persistent

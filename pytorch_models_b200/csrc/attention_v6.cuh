@@ -2,21 +2,26 @@
 // pytorch_models/transformer.py:52 with attn_mask=None, dropout_p=0, is_causal = MHA.forward's `causal`).
 //
 // One work item = (batch, head, pair of 128-row query tiles). One persistent CTA per SM loops over items; key/value
-// rows stream through a 3-stage TMA ring in blocks of 128 with an online softmax. The two query tiles ping-pong so
-// the tensor core works on one tile while the other tile's softmax runs. 384 threads:
+// rows stream through a 4-stage TMA ring in blocks of 128 with an online softmax. 384 threads:
 //   warp 0      : TMA producer (Q pair, double-buffered across items; K/V blocks)
-//   warp 1      : tcgen05.mma issuer, one stream across items in the order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
+//   warp 1      : tcgen05.mma issuer, one stream across items in the order  PV0(n) PV1(n) QK0(n+2) QK1(n+2)
 //                   S_t = Q_t K_j^T          -> TMEM, fp32, 128 columns per tile
 //                   O_t (+)= P_t V_j         -> TMEM, 64 columns, accumulated in place; P_t is the TMEM A operand
 //   warps 2..3  : idle (they only complete warpgroup 0 so that it can hand registers to the softmax warpgroups)
 //   warps 4..7  : softmax warpgroup of tile 0, warps 8..11 : tile 1. One thread per query row (= TMEM lane): the
 //                 whole 128-column S row is read ONCE into registers (setmaxnreg gives these warps 208 registers),
-//                 row max, exp2 with the softmax scale folded in, P written back over S as packed bf16.
+//                 row max, exp2 with the softmax scale folded in, P written as packed bf16.
 //                 The maximum is updated lazily (only when a row outgrows 2^8 of head-room), so the accumulator
 //                 in TMEM is rescaled rarely; the normalised output leaves through one TMA store per warp.
+// TMEM per tile (256 columns, two tiles fill the SM's 512): S [0,128) | P [128,192) | O [192,256). P has its own
+// columns instead of aliasing S (round 1), so a tile's S buffer is free again as soon as its softmax warps hold the
+// row in registers: they arrive on S_EMPTY right after the TMEM loads, and the issuer puts the NEXT block's
+// S = Q K^T into the buffer while the exponentials of the current block are still being computed. The softmax warps
+// therefore never wait for the P.V -> Q.K round trip of the tensor core (round 1: ~1400 of ~3800 clocks per block).
 // Q/K/V are read straight out of the fused QKV activation [rows, 3d] through strided 3-D tensor maps (no head
 // transpose is materialised); the output is written head-interleaved as [rows, d] for out_proj.
 #pragma once
+// EXPERIMENTAL (round 2): not included by the library build unless -DATT_V6; see DESIGN.md section 3.2 for the measurements.
 #include "ptx.cuh"
 
 namespace b200 {
@@ -26,7 +31,15 @@ constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_THREADS = 384;  // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1, 2: softmax
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
-constexpr int ATT_KV_STAGES = 3;
+#ifndef ATT_MMA_ORDER
+#define ATT_MMA_ORDER 0  // 0: PV0 PV1 QK0 QK1 per block (shipped); 1: PV0 QK0 PV1 QK1 (measured slower at L=197)
+#endif
+#ifndef ATT_KV_STAGES
+#define ATT_KV_STAGES 4  // blocks n .. n+2 are live in the issuer's stream (P.V of n, Q.K of n+2) + one being fetched
+#endif
+constexpr int ATT_TM_TILE = 256;  // TMEM columns per query tile
+constexpr int ATT_TM_P = 128;     //   P (bf16 pairs) at [128, 192)
+constexpr int ATT_TM_O = 192;     //   O accumulator at [192, 256)
 constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
 constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
 constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
@@ -65,8 +78,24 @@ struct AttnParams {
       ++tr_n;                                                                   \
     }                                                                           \
   } while (0)
+struct AttTrace {  // handle for events recorded inside softmax_block (one designated lane per softmax warpgroup)
+  long long* buf;
+  int role;
+  int* n;
+  bool on;
+  __device__ __forceinline__ void ev(int e) const {
+    if (on && buf != nullptr && blockIdx.x == 0 && *n < 1000) {
+      buf[2 * (role * 1000 + *n)] = e;
+      buf[2 * (role * 1000 + *n) + 1] = clock64();
+      ++*n;
+    }
+  }
+};
+#define ATT_TR(tr, e) (tr).ev(e)
 #else
 #define ATT_EV(ev) do {} while (0)
+struct AttTrace {};
+#define ATT_TR(tr, e) do {} while (0)
 #endif
 
 // One 128-column block of the online softmax for one query row (= one thread = one TMEM lane).
@@ -99,53 +128,84 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 
 // kBias: x = s * c + bias * log2(e) is formed right after the load (bias_row points at this row's bias for the
 // block's first column, n_cols = valid columns of the block) and the rest runs with c = 1.
+// The row arrives in two halves (two tcgen05.ld each, one wait each) so that the maximum of the first 64 columns is
+// formed while the second half is still on its way; as soon as the whole row is in registers the warp arrives on
+// `bar_s_empty`: the issuer may overwrite S with the next block's scores. P is written to its own columns `tP`, which
+// the previous block's P.V may still be reading: `o_parity` >= 0 names the phase of `bar_o_full` that marks its
+// completion (also what a rescale of O needs), < 0 = nothing to wait for (first block of a tile).
+struct SoftmaxSync {
+  uint32_t bar_s_empty, bar_o_full;
+  int o_parity;
+  unsigned int* abort_word;
+  uint32_t turn_mine, turn_other;  // shared-memory words of the exponential-phase hand-over (see below)
+  AttTrace tr;
+};
+
+// The two softmax warps of an SM sub-partition (same TMEM lane quarter, one per query tile) share one MUFU pipe.
+// Left alone they fall into lockstep — both in their exponential phase, then both in their MUFU-free phases (TMEM
+// load, row maximum, TMEM store, barrier round trips: ~1700 of ~3650 clocks per block in the round-2 event trace),
+// during which the pipe idles. A purely advisory hand-over keeps them in anti-phase instead: a warp entering its
+// exponential phase first waits (bounded, no correctness role) while the other warp's "busy" word is set.
+#ifndef ATT_TURN_SPINS
+#define ATT_TURN_SPINS 96  // x ~30 clocks per probe: gives up after ~3000 clocks (longer than any exponential phase)
+#endif
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <bool kBias>
-__device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool masked, int lim, float c, float& m,
-                                              float& l, float& alpha, bool& rescale, const float* bias_row = nullptr,
-                                              int n_cols = 0) {
+__device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const SoftmaxSync sy, int n_chunks, bool masked,
+                                              int lim, float c, float& m, float& l, float& alpha, bool& rescale,
+                                              const float* bias_row = nullptr, int n_cols = 0) {
   uint32_t v[4][32];
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  const float c_in = c;
+  auto prep_max = [&](int ch) {  // bias, mask and running maximum of one 32-column chunk (ch is a literal after unrolling)
+    if (kBias) {
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch)
-    if (ch < n_chunks) tmem_ld32(tS + ch * 32, v[ch]);
-  tmem_wait_ld();
-  if (kBias) {
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      if (ch < n_chunks) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = ch * 32 + i;
-          const float bv = col < n_cols ? __ldg(bias_row + col) : 0.0f;
-          v[ch][i] = __float_as_uint(fmaf(__uint_as_float(v[ch][i]), c, bv * 1.4426950408889634f));
-        }
+      for (int i = 0; i < 32; ++i) {
+        const int col = ch * 32 + i;
+        const float bv = col < n_cols ? __ldg(bias_row + col) : 0.0f;
+        v[ch][i] = __float_as_uint(fmaf(__uint_as_float(v[ch][i]), c_in, bv * 1.4426950408889634f));
       }
     }
-    c = 1.0f;
-  }
-  if (masked) {
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
+    if (masked) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (ch * 32 + i >= lim) v[ch][i] = 0xff800000u;
-  }
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    if (ch < n_chunks) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[ch][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[ch][i + 1]));
-      }
     }
-  }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      mx0 = fmaxf(mx0, __uint_as_float(v[ch][i]));
+      mx1 = fmaxf(mx1, __uint_as_float(v[ch][i + 1]));
+    }
+  };
+  tmem_ld32(tS, v[0]);
+  if (1 < n_chunks) tmem_ld32(tS + 32, v[1]);
+  tmem_wait_ld();
+  if (2 < n_chunks) tmem_ld32(tS + 64, v[2]);
+  if (3 < n_chunks) tmem_ld32(tS + 96, v[3]);
+  prep_max(0);
+  if (1 < n_chunks) prep_max(1);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane_id() == 0) mbar_arrive(sy.bar_s_empty);
+  ATT_TR(sy.tr, 201);
+  if (2 < n_chunks) prep_max(2);
+  if (3 < n_chunks) prep_max(3);
+  if (kBias) c = 1.0f;
   const float m_new = fmaxf(m, fmaxf(mx0, mx1));
   // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
-  // the first block, where m = -inf)
+  // the first block with a visible key, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
   if (rescale) {
-    alpha = fast_exp2((m - m_new) * c);
+    alpha = fast_exp2((m - m_new) * c);  // m = -inf: 0 (nothing accumulated yet, or only fully masked blocks)
     m = m_new;
     l *= alpha;
   }
@@ -154,6 +214,12 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
   const float m_off = m == -INFINITY ? 0.0f : m;
   const float2 c2 = make_float2(c, c);
   const float2 nmc2 = make_float2(-m_off * c, -m_off * c);
+#if ATT_TURN_SPINS > 0
+  for (int spin = 0; spin < ATT_TURN_SPINS && lds_volatile(sy.turn_other) != 0u; ++spin) {
+  }
+  if (lane_id() == 0) sts_volatile(sy.turn_mine, 1u);
+#endif
+  ATT_TR(sy.tr, 202);
   float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
@@ -172,11 +238,21 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
         if (i & 1) sum1 = __fadd2_rn(sum1, pr); else sum0 = __fadd2_rn(sum0, pr);
         pk[i] = pack_bf16x2(pr.x, pr.y);
       }
-      tmem_st16(tS + ch * 16, pk);
+      if (ch == 0 && sy.o_parity >= 0) {
+        // P.V of the previous block has finished: P's columns are free and O is complete. It was issued a whole
+        // block ago; the wait sits here, after the first chunk's exponentials, so that its latency is covered.
+        mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), sy.abort_word);
+        tc_fence_after();
+      }
+      tmem_st16(tP + ch * 16, pk);
     }
   }
+#if ATT_TURN_SPINS > 0
+  if (lane_id() == 0) sts_volatile(sy.turn_mine, 0u);
+#endif
   const float2 sum = __fadd2_rn(sum0, sum1);
   l += sum.x + sum.y;
+  ATT_TR(sy.tr, 203);
 }
 
 template <bool kBias>
@@ -187,11 +263,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + ATT_SMEM_BAR;
-  // barrier slots: q_full[2] 0..1, q_empty[2] 2..3, kv_full[3] 4..6, kv_empty[3] 7..9,
-  //                s_full[2] 10..11, p_full[2] 12..13, o_full[2] 14..15
+  // barrier slots: q_full[2], q_empty[2], s_full[2], s_empty[2], p_full[2], o_full[2], kv_full[stages], kv_empty[stages]
   auto bar = [&](int i) { return bars + 8u * i; };
-  constexpr int Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = 7, S_FULL = 10, P_FULL = 12, O_FULL = 14;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * 16);
+  constexpr int Q_FULL = 0, Q_EMPTY = 2, S_FULL = 4, S_EMPTY = 6, P_FULL = 8, O_FULL = 10, KV_FULL = 12,
+                KV_EMPTY = 12 + ATT_KV_STAGES;
+  static_assert(8 * (12 + 2 * ATT_KV_STAGES) + 4 <= 224, "barrier block overflows into the hand-over words");
+  const uint32_t turns = sbase + ATT_SMEM_BAR + 224;  // 8 words: busy[tile][lane quarter]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * (12 + 2 * ATT_KV_STAGES));
+  unsigned int* const abw = p.abort_word;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,7 +279,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int tr_role = warp == 0 ? 0 : warp == 1 ? 1 : warp < 8 ? 2 : 3;
 #endif
 
-  unsigned int* const abw = p.abort_word;
   if (sbase & 1023u) {  // the 128B swizzle needs 1024-aligned tiles: report through the status word, never trap
     if (threadIdx.x == 0 && abw != nullptr) *reinterpret_cast<volatile unsigned int*>(abw) = 0xB200A117u;
     return;
@@ -210,6 +288,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(bar(Q_FULL + i), 1);
       mbar_init(bar(Q_EMPTY + i), 1);
       mbar_init(bar(S_FULL + i), 1);
+      mbar_init(bar(S_EMPTY + i), 4);
       mbar_init(bar(P_FULL + i), 4);
       mbar_init(bar(O_FULL + i), 1);
     }
@@ -217,6 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(bar(KV_FULL + s), 1);
       mbar_init(bar(KV_EMPTY + s), 1);
     }
+    for (int i = 0; i < 8; ++i) sts_volatile(turns + 4u * i, 0u);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -231,7 +311,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O accumulator at t*256 + [128,192)
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
   // K/V blocks a query tile has to visit: all of them, or with a causal mask only those up to its last row's diagonal
   auto tile_blocks = [&](int item, int t) {
@@ -279,10 +358,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
     {
-      // The (item, kv-block) sequence of this CTA is walked as ONE stream: while block `cur` is being finished
-      // (PV0, PV1) the score MMAs of the following block `nxt` — possibly the first block of the next item — are
-      // already issued, so a tile's softmax never waits for the other tile's tail.
-      uint32_t g[2] = {0, 0};  // blocks issued so far per tile (barrier parity, O buffer)
+      // The (item, kv-block) sequence of this CTA is walked as ONE stream of blocks n = 0, 1, 2, ...: while block n is
+      // being finished (P.V of both tiles) the scores of block n+2 — possibly of the next item — are issued into the
+      // S buffers that the softmax warps released when they pulled block n+1 into registers. Per tile the order is
+      // QK(n+1) PV(n) QK(n+2) PV(n+1) ..., each waiting on an event of that tile's softmax warps in the order in which
+      // they occur (S_EMPTY(n+1) before P_FULL(n+1)), so the stream never waits on something that needs a later MMA.
+      uint32_t nqk[2] = {0, 0};  // score MMAs issued so far per tile (S_EMPTY parity)
+      uint32_t npv[2] = {0, 0};  // P.V MMAs issued so far per tile (P_FULL parity)
       const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
       struct Blk {
         int item, j;
@@ -296,6 +378,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
       auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
       auto issue_qk = [&](const Blk& bl, int t) {
+        if (nqk[t] > 0) {  // the softmax warps of this tile hold the previous scores in registers
+          mbar_wait(bar(S_EMPTY + t), (nqk[t] - 1) & 1u, abw);
+          tc_fence_after();
+        }
         const uint32_t sq = sbase + ATT_SMEM_Q + (bl.it & 1u) * 2 * ATT_TILE_BYTES + t * ATT_TILE_BYTES;
         const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
         const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + bl.stage * ATT_TILE_BYTES, 16, 1024);
@@ -303,21 +389,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_ss(tmem_base + t * ATT_TM_TILE, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
           umma_commit(bar(S_FULL + t));
         }
         __syncwarp();
+        ++nqk[t];
         if (lane == 0) ATT_EV(100 + t);
       };
       auto issue_pv = [&](const Blk& bl, int t) {
-        mbar_wait(bar(P_FULL + t), g[t] & 1u, abw);
+        mbar_wait(bar(P_FULL + t), npv[t] & 1u, abw);
         if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
         // descriptors are built outside the elected branch (uniform registers); per K step only immediates change:
         // V is MN-major (head_dim contiguous): 16 kv rows = 2048 bytes (+128 in the descriptor); P: 8 TMEM columns
         const uint64_t dv0 = make_smem_desc_sw128(sbase + ATT_SMEM_V + bl.stage * ATT_TILE_BYTES, 16, 1024);
-        const uint32_t pa0 = tmem_base + t * 256;
-        const uint32_t d_o = tmem_base + t * 256 + 128;
+        const uint32_t pa0 = tmem_base + t * ATT_TM_TILE + ATT_TM_P;
+        const uint32_t d_o = tmem_base + t * ATT_TM_TILE + ATT_TM_O;
         const uint32_t acc0 = bl.j > 0 ? 1u : 0u;  // the first block of a tile overwrites O, later ones accumulate
         const int ksteps = n_mma_of(bl.j) / 16;
         if (elect_one()) {
@@ -328,7 +415,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
         if (lane == 0) ATT_EV(120 + t);
-        ++g[t];
+        ++npv[t];
       };
       // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
       auto start_block = [&](const Blk& bl, int t_first, int t_last) {
@@ -364,17 +451,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (cur.item < p.n_items) {
         set_item(cur);
         start_block(cur, 0, 1);
+        Blk nx1 = advance(cur);
+        bool have1 = nx1.item < p.n_items;
+        if (have1) start_block(nx1, 0, 1);
         while (true) {
-          const Blk nxt = advance(cur);
-          const bool more = nxt.item < p.n_items;
+          Blk nx2 = nx1;
+          bool have2 = false;
+          if (have1) {
+            nx2 = advance(nx1);
+            have2 = nx2.item < p.n_items;
+          }
+#if ATT_MMA_ORDER == 0
+          // P.V of both tiles first: a tile that has published its probabilities (in particular its last ones: the
+          // item's epilogue waits for this P.V) is never queued behind the other tile's S_EMPTY, which at an item
+          // boundary only comes after that tile's epilogue. The scores of block n+2 are not needed before the
+          // softmax warps finish block n+1, a whole block from now.
           if (active(cur, 0)) issue_pv(cur, 0);
-          if (more) start_block(nxt, 0, 0);
           if (active(cur, 1)) issue_pv(cur, 1);
-          if (more) start_block(nxt, 1, 1);
+          if (have2) start_block(nx2, 0, 1);
+#else
+          if (active(cur, 0)) issue_pv(cur, 0);
+          if (have2) start_block(nx2, 0, 0);
+          if (active(cur, 1)) issue_pv(cur, 1);
+          if (have2) start_block(nx2, 1, 1);
+#endif
           if (elect_one()) umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
           __syncwarp();
-          if (!more) break;
-          cur = nxt;
+          if (!have1) break;
+          cur = nx1;
+          nx1 = nx2;
+          have1 = have2;
         }
       }
     }
@@ -385,8 +491,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int qd = warp & 3;        // TMEM lane quarter
     const int r = qd * 32 + lane;   // row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    const uint32_t tS = tmem_base + t * 256 + lane_off;
-    const uint32_t tO = tS + 128;
+    const uint32_t tS = tmem_base + t * ATT_TM_TILE + lane_off;
+    const uint32_t tP = tS + ATT_TM_P;
+    const uint32_t tO = tS + ATT_TM_O;
     const float c = p.scale_log2e;
     const uint32_t stg = sbase + ATT_SMEM_STG + uint32_t(warp - 4) * ATT_STG_BYTES;  // this warp's 32 x 128 B staging
     uint32_t g = 0;  // blocks processed so far by this tile
@@ -415,24 +522,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         float alpha = 1.0f;
         bool rescale = false;
+        // P.V(j-1) of this tile must have completed before P(j) is written over P(j-1) (and before O is rescaled).
+        // O_FULL cannot be lapped: its next flip needs this warp's P_FULL arrive below.
+#ifdef ATT_TRACE
+        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, abw,
+                             turns + 4u * (t * 4 + qd), turns + 4u * ((t ^ 1) * 4 + qd),
+                             AttTrace{p.trace, tr_role, &tr_n, lane == 0 && qd == 2}};
+#else
+        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, abw,
+                             turns + 4u * (t * 4 + qd), turns + 4u * ((t ^ 1) * 4 + qd), AttTrace{}};
+#endif
         if (warp_live) {
           const bool masked = diag || (nvalid & 31) != 0;
           if (kBias) {
             const float* brow = p.bias + (long long)b * p.bias_b_stride + (long long)h * p.bias_h_stride +
                                 (long long)min(qrow, p.Lq - 1) * p.bias_row_stride + j * ATT_BKV;
-            softmax_block<true>(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale, brow, nvalid);
+            softmax_block<true>(tS, tP, sy, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale, brow, nvalid);
           } else {
-            softmax_block<false>(tS, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
+            softmax_block<false>(tS, tP, sy, (nvalid + 31) >> 5, masked, lim, c, m, l, alpha, rescale);
           }
-        }
-        if (j > 0 && rescale) {  // warp-uniform
-          // P.V(j-1) must have landed before O is rescaled. The parity wait is safe although most blocks skip it:
-          // O_FULL has completed either g-1 or g phases at this point (P.V(j) cannot even be issued before this
-          // warp publishes P(j) below), and the two cases differ in parity. When there is nothing to rescale the
-          // wait is not needed at all: the tensor core accumulates P.V(j) onto O in issue order.
-          mbar_wait(bar(O_FULL + t), (g - 1) & 1u, abw);
-          tc_fence_after();
-          {
+          if (j > 0 && rescale) {  // warp-uniform; P.V(j-1) has landed (softmax_block waited for it)
             uint32_t o0[32], o1[32];
             tmem_ld32(tO, o0);
             tmem_ld32(tO + 32, o1);
@@ -445,6 +554,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_st32(tO, o0);
             tmem_st32(tO + 32, o1);
           }
+        } else {
+          // rows past Lq: nothing to compute, but the protocol is the same (release S, then publish an unused P)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sy.bar_s_empty);
+          if (sy.o_parity >= 0) mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), abw);
         }
         tmem_wait_st();
         tc_fence_before();

@@ -34,14 +34,17 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_STG_BYTES = 32 * 128;  // one staging buffer: 32 rows x 64 bf16
 constexpr int GEMM_SMEM_COLVEC = GEMM_EPI_WARPS * 2 * 128 * 4;  // per warp: bias|c and colsum of its 128 columns
 // smem plan: kCtas == 1: 3 stages x 48 KB + 1 staging buffer per epilogue warp (only used for problems of <= 128 rows)
-//            kCtas == 2: 5 stages x 32 KB + 1 staging buffer per epilogue warp (measured equal to 4 stages + 2 buffers)
-template <int kCtas>
+//            kCtas == 2: 5 stages x 32 KB + 1 staging buffer per epilogue warp, or — residual epilogues — 4 stages +
+//            2 buffers (one per 64-column chunk): there the buffer is claimed BEFORE the chunk's math (the residual is
+//            transposed through it), so with a single buffer the previous chunk's TMA store would have to drain first.
+//            (Round 1 measured 5 + 1 and 4 + 2 equal for the main loop.)
+template <int kCtas, bool kRes = false>
 struct GemmSmem {
-  static constexpr int kStages = kCtas == 2 ? GEMM_STAGES_2CTA : 3;
+  static constexpr int kStages = kCtas == 2 ? (kRes ? 4 : GEMM_STAGES_2CTA) : 3;
   static constexpr int kBRows = GEMM_BN / kCtas;
   static constexpr int kStageBytes = GEMM_A_BYTES + kBRows * GEMM_BK * 2;
   static constexpr int kRing = kStages * kStageBytes;
-  static constexpr int kStgBufs = (kCtas == 2 && GEMM_STAGES_2CTA <= 4) ? 2 : 1;
+  static constexpr int kStgBufs = (kCtas == 2 && kStages <= 4) ? 2 : 1;
   static constexpr int kStg = GEMM_EPI_WARPS * kStgBufs * GEMM_STG_BYTES;
   static constexpr int kBytes = kRing + kStg + GEMM_SMEM_COLVEC + 256;
   static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -70,6 +73,7 @@ struct GemmParams {
   long long out_batch_stride;
   int ldo;
   int debug;  // timing experiments only: bit0 = skip the output store, bit1 = skip the whole epilogue body
+  unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
 };
 
 // erf-GELU: x*Phi(x) = relu(x) - |x| * 2^Q(|x|), Q = degree-6 minimax fit of log2(0.5*erfc(t/sqrt2)) on [0,6]
@@ -114,7 +118,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
-  using SM = GemmSmem<kCtas>;
+  using SM = GemmSmem<kCtas, kRes>;
   const uint32_t ring = smem_base;
   float* colvec = reinterpret_cast<float*>(smem + SM::kRing + SM::kStg);
   const uint32_t bars = smem_base + SM::kRing + SM::kStg + GEMM_SMEM_COLVEC;
@@ -135,11 +139,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
 
+  if (smem_base & 1023u) {  // the 128B swizzle needs a 1024-aligned ring: report through the status word, never trap
+    if (threadIdx.x == 0 && p.abort_word != nullptr) *reinterpret_cast<volatile unsigned int*>(p.abort_word) = 0xB200A116u;
+    return;  // uniform over the CTA (and over a CTA pair: both CTAs see the same shared-memory layout)
+  }
   if (threadIdx.x == 0) {
-    if (smem_base & 1023u) {
-      printf("gemm_bf16_kernel: dynamic smem base not 1024-aligned (%u)\n", smem_base);
-      __trap();
-    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);   // the leader's producer arrives (expect_tx covers both CTAs' bytes)
       mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when kCtas == 2)
@@ -183,7 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;
       const int n0 = (r % p.tiles_n) * GEMM_BN + int(cta_rank) * kBRows;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_word);
         const uint32_t sa = ring + stage * kStageBytes;
         if (elect_one()) {
           if (kCtas == 2) {
@@ -211,11 +215,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.abort_word);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(full_bar(stage), phase, p.abort_word);
           tc_fence_after();
           const uint32_t sa = ring + stage * kStageBytes;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
@@ -283,16 +287,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (t < p.stat_parts) st_part[t] = __ldg(p.rowstats + grow * p.stat_parts + t);
         }
       }
+      // Residual tile of this warp (32 rows x 128 columns), fetched COALESCED: per 64-column chunk, load j of lane l
+      // reads the 16 bytes at (row 4j + l/8, piece l%8), so one warp instruction covers 4 rows x 128 contiguous bytes
+      // (whole 32-byte sectors; the round-1 form — every lane its own row — used half of each sector it pulled over
+      // the L2 -> SM path, the tightest resource of the N = K = 768 GEMM). The lanes swap to row ownership through
+      // the warp's staging buffer just before the values are needed (see below).
       uint4 rres[2][8];
       if (kRes) {
-        const __nv_bfloat16* res_row = p.res + (long long)b * p.res_batch_stride + (long long)row * p.ldr + nh;
+        const __nv_bfloat16* res_base = p.res + (long long)b * p.res_batch_stride + nh;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const int rr = m0 + q * 32 + 4 * j + (lane >> 3);
+            const int col = cc * 64 + (lane & 7) * 8;
             rres[cc][j] = make_uint4(0, 0, 0, 0);
-            if (row_ok && nh + cc * 64 + j * 8 < p.N)
-              rres[cc][j] = __ldg(reinterpret_cast<const uint4*>(res_row + cc * 64) + j);
+            if (rr < p.M && nh + col < p.N)
+              rres[cc][j] = __ldg(reinterpret_cast<const uint4*>(res_base + (long long)rr * p.ldr + col));
           }
       }
 
@@ -328,7 +339,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float2 st_s1 = make_float2(0.f, 0.f), st_s2 = make_float2(0.f, 0.f);
       bool released = false;
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(acc), acc_phase, p.abort_word);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * GEMM_BN + hf * 128 + (uint32_t(q * 32) << 16);
 
@@ -350,6 +361,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           released = true;
         }
 
+        uint4 own[8];  // this lane's row of the residual chunk (kRes only)
+        if (kRes) {
+          constexpr int kBufOffR = SM::kStgBufs == 2 ? GEMM_STG_BYTES : 0;
+          if (kTmaStore) {  // the TMA store that last used this staging buffer has finished reading it
+            if (elect_one()) tma_store_wait_read<SM::kStgBufs - 1>();
+            __syncwarp();
+          }
+          uint8_t* tb = stg_ptr + cc * kBufOffR;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rw = 4 * j + (lane >> 3);
+            *reinterpret_cast<uint4*>(tb + rw * 128 + (((lane & 7) ^ (rw & 7)) << 4)) = rres[cc][j];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) own[j] = *reinterpret_cast<const uint4*>(tb + lane * 128 + ((j ^ (lane & 7)) << 4));
+          // no second barrier: from here on every lane touches only the 128 bytes of its own row
+        }
         uint32_t packed[32];
         const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
 #pragma unroll
@@ -372,7 +401,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (kAct == 3) x[u] = make_float2(fmaxf(x[u].x, 0.0f), fmaxf(x[u].y, 0.0f));
             if (kAct == 4) x[u] = silu_fast2(x[u]);
             if (kRes) {
-              const uint32_t rr = reinterpret_cast<const uint32_t*>(rres[cc])[2 * j4 + u];
+              const uint32_t rr = reinterpret_cast<const uint32_t*>(own)[2 * j4 + u];
               x[u] = __fadd2_rn(x[u], make_float2(bf16_lo(rr), bf16_hi(rr)));
             }
             packed[2 * j4 + u] = pack_bf16x2(x[u].x, x[u].y);
@@ -398,8 +427,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kTmaStore) {
           // with two buffers the store that last used this one was issued a whole tile ago: no drain on the critical path
           constexpr int kBufOff = SM::kStgBufs == 2 ? GEMM_STG_BYTES : 0;
-          if (elect_one()) tma_store_wait_read<SM::kStgBufs - 1>();
-          __syncwarp();
+          if (!kRes) {  // (with a residual the buffer was already claimed for the transposition above)
+            if (elect_one()) tma_store_wait_read<SM::kStgBufs - 1>();
+            __syncwarp();
+          }
           uint8_t* dst = stg_ptr + cc * kBufOff + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -1,4 +1,5 @@
-// Host-side helpers shared by the C-ABI entry points: error reporting and CUtensorMap construction.
+// Host-side helpers shared by the C-ABI entry points: error reporting, CUtensorMap construction (cached), the
+// per-device SM count and the abort word that bounded device-side waits raise (ptx.cuh: mbar_wait).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -25,10 +26,33 @@ int set_error(int code, const char* fmt, ...);
 
 // Row-major bf16 tensor viewed as up to 3 dims (inner, rows, batches); strides in elements.
 // box = (box_inner, box_rows, 1). swizzle_bytes in {0, 32, 64, 128}.
+// Encoded maps are kept in a process-wide cache keyed by every argument (pointer, shape, strides, box, swizzle): a
+// CUtensorMap is a pure function of those, so the cache never goes stale and a forward pass that reuses its buffers
+// (the caching allocator hands the same blocks back) encodes each map once.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
                    uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows,
                    int swizzle_bytes);
 
+// General form (rank <= 5): dims / box in elements, strides[i] = byte stride of dim i+1. Same cache.
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes);
+
+struct TmapCacheStats {
+  unsigned long long hits, misses;
+};
+TmapCacheStats tmap_cache_stats();
+
+// SM count of the CURRENT device (cached per device ordinal).
 int sm_count();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch.
+int ensure_dynamic_smem(const void* kernel, int bytes);
+
+// The abort word: one unsigned int in mapped, portable host memory (readable by the host without synchronising,
+// writable by every device). 0 = healthy. Device-side waits that exceed their time limit store a non-zero code; every
+// entry point calls check_abort() first and refuses to enqueue more work once it is set.
+unsigned int* abort_word();  // device-usable pointer (UVA); nullptr if the allocation failed
+int check_abort(const char* who);
+unsigned int read_abort_word(bool clear);
 
 }  // namespace b200

@@ -64,8 +64,42 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait. A protocol slip (or a fault in another role) must not hang the GPU: after B200_WAIT_LIMIT_NS of
+// polling the waiter raises the library's abort word (mapped host memory, see host_util.cu) and carries on; every
+// other wait of every CTA then falls through once it sees the word, so the kernel drains in bounded time with
+// garbage results, and the next C-ABI call returns an error instead of enqueueing more work. `abort_word` == nullptr
+// (stand-alone tools) waits forever like a plain spin.
+// The abort word lives across PCIe: it is looked at only by waits that have already lasted B200_WAIT_WATCH_NS — far
+// longer than any wait of a healthy kernel (microseconds) — so the normal path is mbarrier.try_wait and nothing else.
+#ifndef B200_WAIT_LIMIT_NS
+#define B200_WAIT_LIMIT_NS 4000000000ull
+#endif
+#ifndef B200_WAIT_WATCH_NS
+#define B200_WAIT_WATCH_NS 2000000ull
+#endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* abort_word) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0u && abort_word != nullptr) {  // every 1024 failed probes (each suspends in hardware)
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > B200_WAIT_WATCH_NS) {
+        if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) return;
+        if (now - t0 > B200_WAIT_LIMIT_NS) {
+          *reinterpret_cast<volatile unsigned int*>(abort_word) = 0xB200DEADu;
+          __threadfence_system();
+          return;
+        }
+      }
+    }
   }
 }
 

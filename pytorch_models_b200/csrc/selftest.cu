@@ -454,6 +454,13 @@ static const AttnCase kAttnCases[] = {
     {"perf_vitb_smem", 128, 12, 197, 197, true, true, 1.0f, 2, 20},
     {"perf_whisper", 8, 20, 1500, 1500, true, false, 1.0f, 1, 10},
     {"perf_siglip", 32, 16, 576, 576, true, false, 1.0f, 1, 10},
+    // full-batch shapes of BASELINE configs C2..C5 (one GPU): what one attention launch of the bench processes
+    {"perf_vitb_b1024", 1024, 12, 197, 197, true, false, 1.0f, 2, 10},
+    {"perf_siglip_b256", 256, 16, 576, 576, true, false, 1.0f, 1, 5},
+    {"perf_dinov2_b128", 128, 16, 1370, 1370, true, false, 1.0f, 1, 5},
+    {"perf_whisper_b64", 64, 20, 1500, 1500, true, false, 1.0f, 1, 5},
+    {"l1500_wide", 1, 3, 1500, 1500, true, false, 4.0f, 0, 0},
+    {"causal_l1100", 2, 2, 1100, 1100, true, true, 3.0f, 0, 0},
 };
 
 #ifdef ATT_TRACE

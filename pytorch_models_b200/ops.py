@@ -24,37 +24,51 @@ def profile(enable: bool) -> list | None:
     return _PROFILE
 
 
-def _call(name: str, meta: dict | None, *args) -> None:
+def _call(name: str, meta: dict | None, dev: torch.device, *args) -> None:
+    """Enqueue one entry point on ``dev``'s current stream (appended as the last argument). The library launches on
+    the CUDA runtime's current device, so a tensor that lives on another GPU than the current one (``model.to("cuda:1")``
+    without ``torch.cuda.set_device``) switches the device for the duration of the call."""
     global LAUNCHES
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call(name, meta, dev, *args)
     fn = getattr(_lib.load(), name)
+    stream = torch.cuda.current_stream(dev)
     rec = _PROFILE
     if rec is None:
-        rc = fn(*args)
+        rc = fn(*args, stream.cuda_stream)
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = fn(*args)
-        e1.record()
+        e0.record(stream)
+        rc = fn(*args, stream.cuda_stream)
+        e1.record(stream)
         rec.append((name, meta, e0, e1))
     LAUNCHES += 1
     _lib.check(rc, name)
-
-
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
 
 
 def _ptr(t: Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def _need_cuda(*ts: Tensor | None) -> None:
+def _need_cuda(*ts: Tensor | None) -> torch.device:
+    """All tensors must live on one CUDA device; returns it."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "pytorch_models_b200 runs only on CUDA (sm_100a) tensors; there is no CPU fallback "
                 f"(got a {t.device} tensor)"
             )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors of one kernel call live on different devices ({dev} and {t.device})")
+    if dev is None:
+        raise RuntimeError("no tensor arguments")
+    return dev
 
 
 def _need(t: Tensor | None, dtype: torch.dtype, name: str) -> None:
@@ -88,11 +102,10 @@ def linear(
     (then ``ln_eps`` is required). ``stats_out``: (batches*M, ceil(N/128), 2) fp32, needs a residual epilogue; with
     ``stats_rows`` > 0 it is (batches*stats_rows, ceil(N/128), 2) and row (b, m) goes to b*stats_rows + stats_row_offset + m.
     """
-    _need_cuda(x, w, bias, out, colsum, rowstats, residual)
+    dev = _need_cuda(x, w, bias, out, colsum, rowstats, residual, stats_out)
     _need(x, torch.bfloat16, "x"), _need(w, torch.bfloat16, "w"), _need(out, torch.bfloat16, "out")
     _need(bias, torch.float32, "bias"), _need(colsum, torch.float32, "colsum"), _need(rowstats, torch.float32, "rowstats")
     _need(residual, torch.bfloat16, "residual"), _need(stats_out, torch.float32, "stats_out")
-    _need_cuda(stats_out)
     if x.dim() == 2:
         x, out = x.unsqueeze(0), out.unsqueeze(0)
         residual = None if residual is None else residual.unsqueeze(0)
@@ -131,7 +144,7 @@ def linear(
     )
     _call(
         "b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=colsum is not None, gelu=gelu, res=residual is not None),
-        ctypes.byref(args), _stream(),
+        dev, ctypes.byref(args),
     )
     return out
 
@@ -143,7 +156,7 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
     ``causal``: query i sees keys 0..i (top-left aligned like ``F.scaled_dot_product_attention(is_causal=True)``).
     ``bias``: fp32 (B, H, Lq, Lkv) view added to the scaled scores (``attn_mask`` of SDPA); broadcast dimensions may
     have stride 0 (``Tensor.expand``), the last stride must be 1."""
-    _need_cuda(q, k, v, out)
+    dev = _need_cuda(q, k, v, out, bias)
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, name)
         if t.dim() != 3 or t.stride(2) != 1:
@@ -155,72 +168,69 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
     if k.shape != v.shape or k.stride() != v.stride() or k.shape[0] != B or k.shape[2] != D or out.shape != q.shape:
         raise ValueError("q/k/v/out shapes or strides are inconsistent")
     if bias is not None:
-        _need_cuda(bias)
         _need(bias, torch.float32, "bias")
         if bias.shape != (B, n_heads, Lq, Lkv) or (Lkv > 1 and bias.stride(3) != 1) or min(bias.stride()) < 0:
             raise ValueError(f"bias must be a (B, H, Lq, Lkv) = {(B, n_heads, Lq, Lkv)} view with unit inner stride")
         _call(
-            "b200enc_attention_bias", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal), bias=True),
+            "b200enc_attention_bias", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal), bias=True), dev,
             q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1),
             out.data_ptr(), out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
             _lib.ATTN_CAUSAL if causal else 0, bias.data_ptr(), bias.stride(0), bias.stride(1), bias.stride(2),
-            _stream(),
         )
         return out
     _call(
-        "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal)),
+        "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal)), dev,
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),
         out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
-        _lib.ATTN_CAUSAL if causal else 0, _stream(),
+        _lib.ATTN_CAUSAL if causal else 0,
     )
     return out
 
 
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, out: Tensor, stats: Tensor | None = None) -> Tensor:
     """x: (rows, d) view (any row stride), out: (rows, d)."""
-    _need_cuda(x, gamma, beta, out, stats)
+    dev = _need_cuda(x, gamma, beta, out, stats)
     _need(x, torch.bfloat16, "x"), _need(out, torch.bfloat16, "out")
     _need(gamma, torch.float32, "gamma"), _need(beta, torch.float32, "beta"), _need(stats, torch.float32, "stats")
     rows, d = x.shape
     if x.stride(1) != 1 or out.stride(1) != 1 or out.shape != x.shape:
         raise ValueError("layernorm expects (rows, d) views with unit inner stride")
     _call(
-        "b200enc_layernorm", dict(rows=rows, d=d),
+        "b200enc_layernorm", dict(rows=rows, d=d), dev,
         x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps), rows, d, out.data_ptr(),
-        out.stride(0), _ptr(stats), _stream(),
+        out.stride(0), _ptr(stats),
     )
     return out
 
 
 def row_stats(x: Tensor, eps: float, stats: Tensor) -> Tensor:
-    _need_cuda(x, stats)
+    dev = _need_cuda(x, stats)
     _need(x, torch.bfloat16, "x"), _need(stats, torch.float32, "stats")
     rows, d = x.shape
     if x.stride(1) != 1 or stats.numel() != 2 * rows or not stats.is_contiguous():
         raise ValueError("row_stats expects a (rows, d) view and a contiguous (rows, 2) stats tensor")
     _call(
-        "b200enc_row_stats", dict(rows=rows, d=d),
-        x.data_ptr(), x.stride(0), float(eps), rows, d, stats.data_ptr(), _stream()
+        "b200enc_row_stats", dict(rows=rows, d=d), dev,
+        x.data_ptr(), x.stride(0), float(eps), rows, d, stats.data_ptr(),
     )
     return stats
 
 
 def mean_tokens(x: Tensor, out: Tensor) -> Tensor:
-    _need_cuda(x, out)
+    dev = _need_cuda(x, out)
     _need(x, torch.bfloat16, "x"), _need(out, torch.bfloat16, "out")
     B, L, d = x.shape
     if x.stride(2) != 1 or out.shape != (B, d) or out.stride(1) != 1:
         raise ValueError("mean_tokens expects x (B, L, d) and out (B, d)")
     _call(
-        "b200enc_mean_tokens", None,
+        "b200enc_mean_tokens", dict(B=B, L=L, d=d), dev,
         x.data_ptr(), x.stride(0), x.stride(1), B, L, d, out.data_ptr(), out.stride(0),
-                                         _stream()
     )
     return out
 
 
 def patch_rows(imgs: Tensor, patch: int, kpad: int, rows: Tensor) -> Tensor:
-    _need_cuda(imgs, rows)
+    dev = _need_cuda(imgs, rows)
     if imgs.dtype == torch.bfloat16:
         dt = _lib.DTYPE_BF16
     elif imgs.dtype == torch.float32:
@@ -232,19 +242,19 @@ def patch_rows(imgs: Tensor, patch: int, kpad: int, rows: Tensor) -> Tensor:
     _need(rows, torch.bfloat16, "rows")
     B, _, H, W = imgs.shape
     _call(
-        "b200enc_patch_rows", None,
-        imgs.data_ptr(), dt, B, H, W, patch, kpad, rows.data_ptr(), _stream()
+        "b200enc_patch_rows", dict(B=B, H=H, W=W, p=patch, kpad=kpad, f32=imgs.dtype == torch.float32), dev,
+        imgs.data_ptr(), dt, B, H, W, patch, kpad, rows.data_ptr(),
     )
     return rows
 
 
 def cls_rows(cls: Tensor, tokens: Tensor) -> Tensor:
-    _need_cuda(cls, tokens)
+    dev = _need_cuda(cls, tokens)
     _need(cls, torch.bfloat16, "cls"), _need(tokens, torch.bfloat16, "tokens")
     B, _, d = tokens.shape
     _call(
-        "b200enc_cls_rows", None,
-        cls.data_ptr(), B, d, tokens.data_ptr(), tokens.stride(0), _stream()
+        "b200enc_cls_rows", dict(B=B, d=d), dev,
+        cls.data_ptr(), B, d, tokens.data_ptr(), tokens.stride(0),
     )
     return tokens
 
@@ -252,20 +262,20 @@ def cls_rows(cls: Tensor, tokens: Tensor) -> Tensor:
 def broadcast_row(row: Tensor, dst: Tensor) -> Tensor:
     """dst[b, 0, ...] = row for every b: dst (B, rows, *) fp32 / bf16 contiguous, row = one (*)-shaped slice. The same
     kernel as `cls_rows` (a strided broadcast of raw 16-bit units), used for the class token's LayerNorm statistics."""
-    _need_cuda(row, dst)
+    dev = _need_cuda(row, dst)
     if row.dtype != dst.dtype or not (row.is_contiguous() and dst.is_contiguous()) or dst[0, 0].numel() != row.numel():
         raise ValueError("broadcast_row expects a contiguous row that matches dst[b, 0]")
     units = row.element_size() // 2
     _call(
-        "b200enc_cls_rows", None,
-        row.data_ptr(), dst.shape[0], row.numel() * units, dst.data_ptr(), dst.stride(0) * units, _stream()
+        "b200enc_cls_rows", dict(B=dst.shape[0], d=row.numel() * units), dev,
+        row.data_ptr(), dst.shape[0], row.numel() * units, dst.data_ptr(), dst.stride(0) * units,
     )
     return dst
 
 
 def time_rows(x: Tensor, rows: Tensor) -> Tensor:
     """x: (N, C, T) fp32/bf16 -> rows (N, T + 2, C) bf16 with zero first/last rows (conv padding)."""
-    _need_cuda(x, rows)
+    dev = _need_cuda(x, rows)
     if x.dtype == torch.bfloat16:
         dt = _lib.DTYPE_BF16
     elif x.dtype == torch.float32:
@@ -279,8 +289,8 @@ def time_rows(x: Tensor, rows: Tensor) -> Tensor:
         raise ValueError(f"rows must have shape {(N, T + 2, C)}")
     _need(rows, torch.bfloat16, "rows")
     _call(
-        "b200enc_time_rows", None,
-        x.data_ptr(), dt, N, C, T, rows.data_ptr(), _stream()
+        "b200enc_time_rows", dict(N=N, C=C, T=T), dev,
+        x.data_ptr(), dt, N, C, T, rows.data_ptr(),
     )
     return rows
 
@@ -288,7 +298,7 @@ def time_rows(x: Tensor, rows: Tensor) -> Tensor:
 def embed_rows(ids: Tensor, tok: Tensor, pos: Tensor, out: Tensor) -> Tensor:
     """ids: (B, L) int64, tok: (vocab, d), pos: (>= L, d) [both fp32 or both bf16] -> out (B, L, d) bf16 =
     tok[ids] + pos[:L]. Rows whose id is out of range come back as NaN (device code cannot raise)."""
-    _need_cuda(ids, tok, pos, out)
+    dev = _need_cuda(ids, tok, pos, out)
     _need(ids, torch.int64, "ids"), _need(out, torch.bfloat16, "out")
     if tok.dtype != pos.dtype:
         raise TypeError(f"token and position tables must share a dtype, got {tok.dtype} and {pos.dtype}")
@@ -307,8 +317,8 @@ def embed_rows(ids: Tensor, tok: Tensor, pos: Tensor, out: Tensor) -> Tensor:
     if B * L == 0:
         return out
     _call(
-        "b200enc_embed_rows", None,
-        ids.data_ptr(), B * L, L, tok.data_ptr(), pos.data_ptr(), dt, vocab, d, out.data_ptr(), _stream()
+        "b200enc_embed_rows", dict(rows=B * L, d=d), dev,
+        ids.data_ptr(), B * L, L, tok.data_ptr(), pos.data_ptr(), dt, vocab, d, out.data_ptr(),
     )
     return out
 
@@ -316,7 +326,7 @@ def embed_rows(ids: Tensor, tok: Tensor, pos: Tensor, out: Tensor) -> Tensor:
 def whisper_logmel(audio: Tensor, filters_t: Tensor, out: Tensor) -> Tensor:
     """audio: (N, L) fp32, filters_t: (201, n_mels) fp32 (mel filter bank transposed) -> out (N, n_mels, L // 160) fp32:
     the normalised log-mel spectrogram of ``WhisperPreprocessor`` (whisper.py:143-148)."""
-    _need_cuda(audio, filters_t, out)
+    dev = _need_cuda(audio, filters_t, out)
     _need(audio, torch.float32, "audio"), _need(filters_t, torch.float32, "filters_t"), _need(out, torch.float32, "out")
     if audio.dim() != 2 or audio.stride(1) != 1 or not filters_t.is_contiguous() or not out.is_contiguous():
         raise ValueError("whisper_logmel expects (N, L) audio with unit inner stride and contiguous filters / output")
@@ -328,8 +338,7 @@ def whisper_logmel(audio: Tensor, filters_t: Tensor, out: Tensor) -> Tensor:
         return out
     scratch = torch.empty(N, device=audio.device, dtype=torch.int32)
     _call(
-        "b200enc_whisper_logmel", None,
+        "b200enc_whisper_logmel", dict(N=N, L=L, n_mels=n_mels), dev,
         audio.data_ptr(), audio.stride(0), N, L, filters_t.data_ptr(), n_mels, out.data_ptr(), scratch.data_ptr(),
-        _stream()
     )
     return out

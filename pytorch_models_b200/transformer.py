@@ -37,13 +37,37 @@ _MAX_STAT_PARTS = 12  # libb200enc combines at most 12 partial statistics per ro
 
 
 # ----------------------------------------------------------------------------------------------- weight packing
+_PACK_EPOCH = 0  # bumped by invalidate_packed(): every kernel-ready copy made before is rebuilt on next use
+
+
+def invalidate_packed() -> None:
+    """Forget every packed (kernel-ready) copy of module parameters in this process.
+
+    The caches key on ``(data_ptr, _version, dtype, device, shape)`` of the source parameters, which sees parameter
+    replacement, ``load_state_dict``, ``copy_`` / ``mul_`` on the parameter (what the reference loaders do,
+    vit.py:172-197,290-304), dtype / device moves and ``resize_pe``. PyTorch keeps NO record of writes made through
+    ``param.data`` (``p.data.copy_(ema)``: ``.data`` carries its own version counter), so after such a write call
+    this function — otherwise the forward keeps using the stale bf16 copies, silently."""
+    global _PACK_EPOCH
+    _PACK_EPOCH += 1
+
+
+def _version(p: Tensor) -> int:
+    try:
+        return p._version
+    except RuntimeError:  # "Inference tensors do not track version counter" (created under torch.inference_mode)
+        return -1
+
+
 def _key(*params: Tensor | None) -> tuple:
-    return tuple(None if p is None else (p.data_ptr(), p._version, p.dtype, p.device) for p in params)
+    return (_PACK_EPOCH,) + tuple(
+        None if p is None else (p.data_ptr(), _version(p), p.dtype, p.device, tuple(p.shape)) for p in params)
 
 
 class _Packed:
     """Kernel-ready copies of a module's parameters, rebuilt whenever a source tensor is replaced or mutated in place
-    (the reference loaders do both: vit.py:172-197 copy_, vit.py:290-304 mul_)."""
+    (the reference loaders do both: vit.py:172-197 copy_, vit.py:290-304 mul_); see `invalidate_packed` for the one
+    kind of write that cannot be seen (through ``.data``)."""
 
     def __init__(self) -> None:
         self.key: tuple | None = None
@@ -160,6 +184,8 @@ class MHA(nn.Module):
         b = b.to(torch.float32)
         if b.dim() > 4:
             b = b.reshape(-1, *b.shape[-3:])
+        if b.shape[-1] == 1 and Lkv > 1:  # broadcast over the keys: the kernel reads consecutive keys, materialise them
+            b = b.expand(*b.shape[:-1], Lkv)
         if b.stride(-1) != 1 and b.shape[-1] > 1:
             b = b.contiguous()
         return b.expand(B, self.n_heads, Lq, Lkv)
@@ -314,7 +340,7 @@ class DecoderLayer(nn.Module):
         self.ca = MHA(d_model, n_heads, head_dim, bias, dropout) if cross_attn else None
         self.mlp_norm = nn.LayerNorm(d_model, norm_eps)
         self.mlp = MLP(d_model, int(d_model * mlp_ratio), dropout, act)
-        self._pqkv, self._pcq = _Packed(), _Packed()
+        self._pqkv, self._pcq, self._pcqkv = _Packed(), _Packed(), _Packed()
 
     # -- packing -------------------------------------------------------------------------------
     def _pack_proj(self, slot: _Packed, lins: list[nn.Linear], norm: nn.LayerNorm) -> SimpleNamespace:
@@ -343,7 +369,11 @@ class DecoderLayer(nn.Module):
         )
         if self.ca is not None:
             ci = self.ca.n_heads * self.ca.head_dim
-            ws.cq, ws.ckv, ws.catt, ws.mid2 = e(B, L, ci), e(B, Lm, 2 * ci), e(B, L, ci), e(M, d)
+            ws.catt, ws.mid2 = e(B, L, ci), e(M, d)
+            if Lm > 0:
+                ws.cq, ws.ckv = e(B, L, ci), e(B, Lm, 2 * ci)
+            else:  # no memory: the reference's MHA falls back to k = v = q (transformer.py:44-45)
+                ws.cqkv = e(B, L, 3 * ci)
             ws.parts_mid2 = e(M, parts, 2, dt=torch.float32) if fused else None
         return ws
 
@@ -368,16 +398,22 @@ class DecoderLayer(nn.Module):
         q, k, v = ws.qkv[:, :, :inner], ws.qkv[:, :, inner:2 * inner], ws.qkv[:, :, 2 * inner:]
         if ca is not None:
             ca.check_supported()
-            if memory3 is None:
-                raise ValueError("a DecoderLayer built with cross_attn=True needs `memory`")
-            if memory3.shape[0] != B or memory3.shape[2] != d or memory3.shape[1] != ws.Lm:
-                raise ValueError(f"memory {tuple(memory3.shape)} does not match the workspace / batch")
             ci = ca.n_heads * ca.head_dim
-            Mm = B * ws.Lm
-            pcq = self._pack_proj(self._pcq, [ca.q_proj], self.ca_norm)
-            pckv = ca._pack("kv", [ca.k_proj, ca.v_proj])
             pco = ca._pack("out", [ca.out_proj])
-            ck, cv = ws.ckv[:, :, :ci], ws.ckv[:, :, ci:]
+            if memory3 is None:
+                # memory=None: MHA.forward(q, None) takes k = v = q (transformer.py:44-45), i.e. the cross-attention
+                # block degenerates to un-masked self-attention with the ca weights on ca_norm(x) (pre-norm) / x
+                if ws.Lm != 0:
+                    raise ValueError("workspace was sized for a memory but none was given")
+                pcqkv = self._pack_proj(self._pcqkv, [ca.q_proj, ca.k_proj, ca.v_proj], self.ca_norm)
+                cq, ck, cv = ws.cqkv[:, :, :ci], ws.cqkv[:, :, ci:2 * ci], ws.cqkv[:, :, 2 * ci:]
+            else:
+                if memory3.shape[0] != B or memory3.shape[2] != d or memory3.shape[1] != ws.Lm:
+                    raise ValueError(f"memory {tuple(memory3.shape)} does not match the workspace / batch")
+                Mm = B * ws.Lm
+                pcq = self._pack_proj(self._pcq, [ca.q_proj], self.ca_norm)
+                pckv = ca._pack("kv", [ca.k_proj, ca.v_proj])
+                cq, ck, cv = ws.cq, ws.ckv[:, :, :ci], ws.ckv[:, :, ci:]
         if self.pre_norm:
             if stats_in is None:
                 stats_in = ops.row_stats(x2, self.sa_norm.eps, ws.stats)
@@ -388,10 +424,14 @@ class DecoderLayer(nn.Module):
             if ca is not None:
                 if mid_stats is None:
                     mid_stats = ops.row_stats(mid, self.ca_norm.eps, ws.stats)
-                ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci), colsum=pcq.colsum, rowstats=mid_stats,
-                           ln_eps=self.ca_norm.eps)
-                ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
-                ops.attention(ws.cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
+                if memory3 is None:
+                    ops.linear(mid, pcqkv.w, pcqkv.bias, ws.cqkv.view(M, 3 * ci), colsum=pcqkv.colsum,
+                               rowstats=mid_stats, ln_eps=self.ca_norm.eps)
+                else:
+                    ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci), colsum=pcq.colsum, rowstats=mid_stats,
+                               ln_eps=self.ca_norm.eps)
+                    ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
+                ops.attention(cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
                 ops.linear(ws.catt.view(M, ci), pco.w, pco.bias, ws.mid2, residual=mid, stats_out=ws.parts_mid2)
                 mid, mid_stats = ws.mid2, ws.parts_mid2
             if mid_stats is None:
@@ -411,9 +451,12 @@ class DecoderLayer(nn.Module):
             mid = ws.mid
             if ca is not None:
                 gc, bc = norm_vectors(self.ca_norm)
-                ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci))
-                ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
-                ops.attention(ws.cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
+                if memory3 is None:
+                    ops.linear(mid, pcqkv.w, pcqkv.bias, ws.cqkv.view(M, 3 * ci))
+                else:
+                    ops.linear(mid, pcq.w, pcq.bias, ws.cq.view(M, ci))
+                    ops.linear(memory3.view(Mm, d), pckv.w, pckv.bias, ws.ckv.view(Mm, 2 * ci))
+                ops.attention(cq, ck, cv, ws.catt, ca.n_heads, ca.scale)
                 ops.linear(ws.catt.view(M, ci), pco.w, pco.bias, ws.tmp, residual=mid)
                 ops.layernorm(ws.tmp, gc, bc, self.ca_norm.eps, ws.mid2)
                 mid = ws.mid2

@@ -3,10 +3,12 @@
  (b) the fp32 CPU oracle on seeded inputs at the BASELINE configs' shapes.
 
 Stated tolerance (SURVEY §8(c) / BASELINE.md §4), for post-LayerNorm outputs with RMS ~ 1, bf16 kernels vs the fp32
-reference: max-abs <= 0.125 for <= 12 layers, <= 0.20 for 24-32 layers, per-sample cosine >= 0.9999. Calibration
-(profiles/r01/parity_report.json, measured on the B200): PyTorch's own bf16 forward of the same math has max-abs
-0.052 / 0.011 / 0.047 / 0.135 on C2 / C3 / C4 / C5 against the same fp32 oracle (ours: 0.049 / 0.009 / 0.047 / 0.135),
-so the 32-layer bound is 1.5x what the library path itself shows; a larger error is a bug, not "bf16 noise".
+reference: max-abs <= 0.125 for <= 12 layers, <= 0.15 for 24-32 layers, per-sample cosine >= 0.9999 — the numbers
+BASELINE.md §4 / SURVEY §8(c) state. Calibration (profiles/r01/parity_report.json, measured on the B200): PyTorch's own
+bf16 forward of the same math has max-abs 0.052 / 0.011 / 0.047 / 0.135 on C2 / C3 / C4 / C5 against the same fp32
+oracle (ours: 0.049 / 0.009 / 0.047 / 0.135); a larger error is a bug, not "bf16 noise". The bound is applied as stated
+to every fixture whose outputs have unit scale; only BERT's post-norm stack (outputs up to |x| ~ 12, SURVEY §8(c):
+the reference's own bf16 error there is 0.31) scales it with the output range.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ from oracle import oracle_torch
 
 pytestmark = pytest.mark.gpu
 
-MAX_ABS_12, MAX_ABS_32, MIN_COS = 0.125, 0.20, 0.9999
+MAX_ABS_12, MAX_ABS_32, MIN_COS = 0.125, 0.15, 0.9999
 
 
 def _run_fixture(g, m):
@@ -56,7 +58,10 @@ def test_against_reference_golden(golden, name, param_dtype):
     got = _run_fixture(g, m)
     for key, expected in g.out.items():
         max_abs, min_cos = error_stats(got[key], expected)
-        scale = max(1.0, float(np.abs(expected).max()) / 4.0)  # BERT post-norm outputs reach |x| ~ 10
+        # unit-scale outputs take the stated bound as is; BERT's post-norm outputs reach |x| ~ 12 and logits are not
+        # normalised at all, so those two kinds scale the bound with the output range (relative bf16 error)
+        scaled = g.hyper["kind"] == "bert" or key == "logits"
+        scale = max(1.0, float(np.abs(expected).max()) / 4.0) if scaled else 1.0
         assert max_abs <= MAX_ABS_12 * scale and min_cos >= MIN_COS, f"{name}.{key}: max_abs={max_abs} cos={min_cos}"
 
 
