@@ -414,6 +414,28 @@ def main() -> None:
         e2e = e2e_leg(torch.bfloat16)
         e2e_f32 = e2e_leg(torch.float32)  # what the reference's callers hold (tests/image/test_vit.py:11)
 
+    # ---- N > 1: the optional NCCL all-gather of the embeddings, once, outside every timed region, checked bit for bit
+    # against the same global batch run on one GPU (no cross-rank arithmetic exists, so it must be exact)
+    gather_check = None
+    if world > 1:
+        from pytorch_models_b200.sharding import gather_embeddings, shard_batch
+
+        n_chk = min(global_cfg, 8 * world)
+        torch.manual_seed(12345)  # the same global batch on every rank
+        xg = torch.randn(n_chk, *cfg["shape"]).bfloat16().to(dev)
+        with torch.no_grad():
+            mine = model(shard_batch(xg, rank, world))
+            t0g = time.perf_counter()
+            gathered = gather_embeddings(mine, total=n_chk)
+            torch.cuda.synchronize()
+            t_gather = time.perf_counter() - t0g
+            whole = model(xg)
+        same = torch.tensor([int(torch.equal(gathered, whole))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        gather_check = {"backend": dist.get_backend(), "samples": n_chk, "bit_identical_on_all_ranks": bool(same.item()),
+                        "bytes_per_rank": mine.numel() * mine.element_size(), "wall_ms_incl_launch": t_gather * 1e3}
+        del xg
+
     # ---- weak-scaled companion figure (N > 1, strong run): every GPU takes the whole configured batch
     weak = None
     if world > 1 and args.scaling == "strong":
@@ -532,7 +554,8 @@ def main() -> None:
             "tokens_per_s": value * cfg["L"],
             "model_tflops": value * fl / 1e12, "model_frac_of_burst_peak": value * fl / 1e12 / world / peaks["burst"],
             "model_frac_of_sustained_peak": value * fl / 1e12 / world / peaks["sustained"],
-            "e2e": e2e, "e2e_fp32_host": e2e_f32, "weak_scaling": weak, "gpu_launches": launches,
+            "e2e": e2e, "e2e_fp32_host": e2e_f32, "weak_scaling": weak, "gather_check": gather_check,
+            "gpu_launches": launches,
             "gpu_launches_per_step": launches_per_step, "clocks": clocks,
             "roofline": roofline, "roofline_attention": roofline_attention, "roofline_rows": roofline_rows,
             "cpu_baseline": cpu_baseline,

@@ -95,6 +95,7 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
 /* flags for b200enc_attention */
 #define B200ENC_ATTN_CAUSAL 1 /* key j only visible to queries i >= j (is_causal=True of SDPA: DecoderLayer, transformer.py:97) */
+#define B200ENC_ATTN_DEBUG_FAULT 65536 /* self-test only: one CTA drops a barrier commit so that the watchdog path runs */
 
 /*
  * out[b][i][64h + :] = softmax_j( q[b][i][64h + :] . k[b][j][64h + :] * scale ) v[b][j][64h + :]

@@ -103,6 +103,8 @@ def check(rc: int, what: str) -> None:
     if rc == 0:
         return
     msg = load().b200enc_last_error().decode("utf-8", "replace")
+    if rc == -3:  # an earlier kernel gave up on a barrier wait: device-side fault, not a caller error
+        raise B200EncError(f"{what}: {msg}")
     if rc < 0:
         raise ValueError(f"{what}: {msg}")
     raise B200EncError(f"{what}: CUDA error {rc}: {msg}")

@@ -71,6 +71,7 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
   p.bias_h_stride = bias_h_stride;
   p.bias_row_stride = bias_row_stride;
   p.abort_word = abort_word();
+  p.debug_fault = (flags >> 16) & 1;  // selftest only (B200ENC_ATTN_DEBUG_FAULT)
 #ifdef ATT_TRACE
   p.trace = g_attention_trace;
 #else

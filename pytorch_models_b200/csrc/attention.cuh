@@ -8,7 +8,12 @@
 //   warp 1      : tcgen05.mma issuer, one stream across items in the order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
 //                   S_t = Q_t K_j^T          -> TMEM, fp32, 128 columns per tile
 //                   O_t (+)= P_t V_j         -> TMEM, 64 columns, accumulated in place; P_t is the TMEM A operand
-//   warps 2..3  : idle (they only complete warpgroup 0 so that it can hand registers to the softmax warpgroups)
+//   warp 2      : watchdog. The working warps spin on their mbarriers with the tightest possible loop (a bounded
+//                 loop costs this kernel 3-7 %, round-2 A/B); the watchdog sleeps on a DONE barrier and, if the CTA's
+//                 progress counter has not moved for B200_WAIT_LIMIT_NS, raises the library's abort word and keeps
+//                 arriving on every protocol barrier, so that every stuck waiter falls through, the roles run out
+//                 of work and the kernel exits (garbage results, reported by the next C-ABI call) instead of hanging
+//   warp 3      : idle (warps 2..3 complete warpgroup 0 so that it can hand registers to the softmax warpgroups)
 //   warps 4..7  : softmax warpgroup of tile 0, warps 8..11 : tile 1. One thread per query row (= TMEM lane): the
 //                 whole 128-column S row is read ONCE into registers (setmaxnreg gives these warps 208 registers),
 //                 row max, exp2 with the softmax scale folded in, P written back over S as packed bf16.
@@ -52,7 +57,8 @@ struct AttnParams {
   const float* bias;
   long long bias_b_stride, bias_h_stride, bias_row_stride;
   long long* trace;   // debug only: (event, clock) records of CTA 0 (nullptr in production)
-  unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
+  unsigned int* abort_word;  // raised by the watchdog warp when the CTA stops making progress; may be nullptr
+  int debug_fault;           // selftest only: 1 = CTA 0 drops one S_FULL commit (a protocol slip) to exercise the watchdog
 };
 
 #ifdef ATT_TRACE
@@ -145,7 +151,9 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
   // the first block, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
   if (rescale) {
-    alpha = fast_exp2((m - m_new) * c);
+    // a row that has not seen a visible key yet (m_new = -inf, additive bias only) has nothing to rescale:
+    // exp2(-inf - -inf) would be NaN and poison l
+    alpha = m_new == -INFINITY ? 1.0f : fast_exp2((m - m_new) * c);
     m = m_new;
     l *= alpha;
   }
@@ -190,8 +198,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // barrier slots: q_full[2] 0..1, q_empty[2] 2..3, kv_full[3] 4..6, kv_empty[3] 7..9,
   //                s_full[2] 10..11, p_full[2] 12..13, o_full[2] 14..15
   auto bar = [&](int i) { return bars + 8u * i; };
-  constexpr int Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = 7, S_FULL = 10, P_FULL = 12, O_FULL = 14;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * 16);
+  constexpr int Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = 7, S_FULL = 10, P_FULL = 12, O_FULL = 14, DONE = 16;
+  constexpr int kProtocolBarriers = 16;  // every barrier below DONE takes part in the data-flow protocol
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * 17);
+  const uint32_t progress_addr = sbase + ATT_SMEM_BAR + 8 * 17 + 4;  // blocks issued by the MMA warp (watchdog input)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,6 +227,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(bar(KV_FULL + s), 1);
       mbar_init(bar(KV_EMPTY + s), 1);
     }
+    mbar_init(bar(DONE), 10);  // producer, MMA issuer and the eight softmax warps arrive when they run out of work
+    *reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * 17 + 4) = 0u;
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -253,7 +265,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int b = bh / p.H;
       const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
       const uint32_t qb = it & 1u;
-      mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u, abw);
+      mbar_wait_plain(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar(Q_FULL + qb), (two ? 2 : 1) * ATT_TILE_BYTES);
         const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
@@ -263,7 +275,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       const int nb = item_blocks(item);
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u, abw);
+        mbar_wait_plain(bar(KV_EMPTY + stage), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
@@ -276,6 +288,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
+    if (lane == 0) mbar_arrive(bar(DONE));
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
     {
@@ -283,6 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // (PV0, PV1) the score MMAs of the following block `nxt` — possibly the first block of the next item — are
       // already issued, so a tile's softmax never waits for the other tile's tail.
       uint32_t g[2] = {0, 0};  // blocks issued so far per tile (barrier parity, O buffer)
+      uint32_t blocks_done = 0;
       const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
       struct Blk {
         int item, j;
@@ -300,17 +314,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
         const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + bl.stage * ATT_TILE_BYTES, 16, 1024);
         const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma_of(bl.j), 0, 0);
+        const bool drop_commit = p.debug_fault == 1 && blockIdx.x == 0 && bl.it == 0 && bl.j == 0 && t == 0;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_HD / 16; ++k)
             umma_ss(tmem_base + t * 256, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(bar(S_FULL + t));
+          if (!drop_commit) umma_commit(bar(S_FULL + t));
         }
         __syncwarp();
         if (lane == 0) ATT_EV(100 + t);
       };
       auto issue_pv = [&](const Blk& bl, int t) {
-        mbar_wait(bar(P_FULL + t), g[t] & 1u, abw);
+        mbar_wait_plain(bar(P_FULL + t), g[t] & 1u);
         if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
         // descriptors are built outside the elected branch (uniform registers); per K step only immediates change:
@@ -333,8 +348,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
       auto start_block = [&](const Blk& bl, int t_first, int t_last) {
         if (t_first == 0) {
-          if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u, abw);
-          mbar_wait(bar(KV_FULL + bl.stage), bl.phase, abw);
+          if (bl.j == 0) mbar_wait_plain(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u);
+          mbar_wait_plain(bar(KV_FULL + bl.stage), bl.phase);
           if (lane == 0) ATT_EV(130);
           tc_fence_after();
         }
@@ -373,8 +388,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (more) start_block(nxt, 1, 1);
           if (elect_one()) umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
           __syncwarp();
+          if (lane == 0) sts_u32_volatile(progress_addr, ++blocks_done);  // the watchdog's sign of life
           if (!more) break;
           cur = nxt;
+        }
+      }
+      if (lane == 0) mbar_arrive(bar(DONE));
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ watchdog (see the header comment)
+    if (abw != nullptr) {
+      uint32_t last = 0xFFFFFFFFu;
+      uint64_t t_last = 0;
+      bool raised = false;
+      while (!mbar_try_wait(bar(DONE), 0u)) {
+        const uint64_t now = global_timer_ns();
+        const uint32_t pr = lds_u32_volatile(progress_addr);
+        if (pr != last || t_last == 0) {
+          last = pr;
+          t_last = now;
+        } else if (now - t_last > B200_WAIT_LIMIT_NS) {
+          if (!raised && lane == 0) {
+            *reinterpret_cast<volatile unsigned int*>(abw) = 0xB200DEADu;
+            __threadfence_system();
+          }
+          raised = true;
+          // flip every protocol barrier, again and again: each stuck waiter gets past its current wait, the roles
+          // walk through the rest of their (now meaningless) work and arrive on DONE
+          if (lane < kProtocolBarriers) {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) mbar_arrive(bar(lane));
+          }
+          __nanosleep(2000);
         }
       }
     }
@@ -410,7 +455,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
         const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
         const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
-        mbar_wait(bar(S_FULL + t), g & 1u, abw);
+        mbar_wait_plain(bar(S_FULL + t), g & 1u);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
         float alpha = 1.0f;
@@ -430,7 +475,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // O_FULL has completed either g-1 or g phases at this point (P.V(j) cannot even be issued before this
           // warp publishes P(j) below), and the two cases differ in parity. When there is nothing to rescale the
           // wait is not needed at all: the tensor core accumulates P.V(j) onto O in issue order.
-          mbar_wait(bar(O_FULL + t), (g - 1) & 1u, abw);
+          mbar_wait_plain(bar(O_FULL + t), (g - 1) & 1u);
           tc_fence_after();
           {
             uint32_t o0[32], o1[32];
@@ -452,7 +497,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
         if (lane == 0 && qd == 2) ATT_EV(210 + t);
       }
-      mbar_wait(bar(O_FULL + t), (g - 1) & 1u, abw);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
+      mbar_wait_plain(bar(O_FULL + t), (g - 1) & 1u);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
       tc_fence_after();
       if (lane == 0 && qd == 2) ATT_EV(220 + t);
       // normalise the 64 output columns of this head and hand the warp's 32 rows to one TMA store (rows >= Lq are
@@ -495,6 +540,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DONE));
   }
 
   tc_fence_before();

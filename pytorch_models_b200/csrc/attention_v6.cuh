@@ -66,6 +66,7 @@ struct AttnParams {
   long long bias_b_stride, bias_h_stride, bias_row_stride;
   long long* trace;   // debug only: (event, clock) records of CTA 0 (nullptr in production)
   unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
+  int debug_fault;           // unused here (attention.cuh: watchdog self-test)
 };
 
 #ifdef ATT_TRACE
@@ -136,7 +137,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 struct SoftmaxSync {
   uint32_t bar_s_empty, bar_o_full;
   int o_parity;
-  unsigned int* abort_word;
+  WaitCtx* wait;
   uint32_t turn_mine, turn_other;  // shared-memory words of the exponential-phase hand-over (see below)
   AttTrace tr;
 };
@@ -146,8 +147,11 @@ struct SoftmaxSync {
 // load, row maximum, TMEM store, barrier round trips: ~1700 of ~3650 clocks per block in the round-2 event trace),
 // during which the pipe idles. A purely advisory hand-over keeps them in anti-phase instead: a warp entering its
 // exponential phase first waits (bounded, no correctness role) while the other warp's "busy" word is set.
+#ifndef ATT_SKEW_CLKS
+#define ATT_SKEW_CLKS 0
+#endif
 #ifndef ATT_TURN_SPINS
-#define ATT_TURN_SPINS 96  // x ~30 clocks per probe: gives up after ~3000 clocks (longer than any exponential phase)
+#define ATT_TURN_SPINS 0  // x ~30 clocks per probe: gives up after ~3000 clocks (longer than any exponential phase)
 #endif
 __device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
   uint32_t v;
@@ -188,11 +192,14 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
   tmem_ld32(tS, v[0]);
   if (1 < n_chunks) tmem_ld32(tS + 32, v[1]);
   tmem_wait_ld();
+  ATT_TR(sy.tr, 301);
   if (2 < n_chunks) tmem_ld32(tS + 64, v[2]);
   if (3 < n_chunks) tmem_ld32(tS + 96, v[3]);
   prep_max(0);
   if (1 < n_chunks) prep_max(1);
+  ATT_TR(sy.tr, 302);
   tmem_wait_ld();
+  ATT_TR(sy.tr, 303);
   tc_fence_before();
   __syncwarp();
   if (lane_id() == 0) mbar_arrive(sy.bar_s_empty);
@@ -201,11 +208,14 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
   if (3 < n_chunks) prep_max(3);
   if (kBias) c = 1.0f;
   const float m_new = fmaxf(m, fmaxf(mx0, mx1));
+  ATT_TR(sy.tr, 304);
   // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
   // the first block with a visible key, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
   if (rescale) {
-    alpha = fast_exp2((m - m_new) * c);  // m = -inf: 0 (nothing accumulated yet, or only fully masked blocks)
+    // m = -inf, m_new finite: 0 (nothing accumulated yet). m_new = -inf (no visible key so far, additive bias only):
+    // nothing to rescale — exp2(-inf - -inf) would be NaN and poison l
+    alpha = m_new == -INFINITY ? 1.0f : fast_exp2((m - m_new) * c);
     m = m_new;
     l *= alpha;
   }
@@ -241,10 +251,14 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
       if (ch == 0 && sy.o_parity >= 0) {
         // P.V of the previous block has finished: P's columns are free and O is complete. It was issued a whole
         // block ago; the wait sits here, after the first chunk's exponentials, so that its latency is covered.
-        mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), sy.abort_word);
+        ATT_TR(sy.tr, 305);
+        mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), *sy.wait);
+        ATT_TR(sy.tr, 306);
         tc_fence_after();
+        ATT_TR(sy.tr, 307);
       }
       tmem_st16(tP + ch * 16, pk);
+      ATT_TR(sy.tr, 310 + ch);
     }
   }
 #if ATT_TURN_SPINS > 0
@@ -271,6 +285,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t turns = sbase + ATT_SMEM_BAR + 224;  // 8 words: busy[tile][lane quarter]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * (12 + 2 * ATT_KV_STAGES));
   unsigned int* const abw = p.abort_word;
+  WaitCtx wctx = make_wait_ctx(abw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -332,7 +347,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int b = bh / p.H;
       const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
       const uint32_t qb = it & 1u;
-      mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u, abw);
+      mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u, wctx);
       if (elect_one()) {
         mbar_expect_tx(bar(Q_FULL + qb), (two ? 2 : 1) * ATT_TILE_BYTES);
         const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
@@ -342,7 +357,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       const int nb = item_blocks(item);
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u, abw);
+        mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u, wctx);
         if (elect_one()) {
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
@@ -379,7 +394,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
       auto issue_qk = [&](const Blk& bl, int t) {
         if (nqk[t] > 0) {  // the softmax warps of this tile hold the previous scores in registers
-          mbar_wait(bar(S_EMPTY + t), (nqk[t] - 1) & 1u, abw);
+          mbar_wait(bar(S_EMPTY + t), (nqk[t] - 1) & 1u, wctx);
           tc_fence_after();
         }
         const uint32_t sq = sbase + ATT_SMEM_Q + (bl.it & 1u) * 2 * ATT_TILE_BYTES + t * ATT_TILE_BYTES;
@@ -397,7 +412,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) ATT_EV(100 + t);
       };
       auto issue_pv = [&](const Blk& bl, int t) {
-        mbar_wait(bar(P_FULL + t), npv[t] & 1u, abw);
+        mbar_wait(bar(P_FULL + t), npv[t] & 1u, wctx);
         if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
         // descriptors are built outside the elected branch (uniform registers); per K step only immediates change:
@@ -420,8 +435,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
       auto start_block = [&](const Blk& bl, int t_first, int t_last) {
         if (t_first == 0) {
-          if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u, abw);
-          mbar_wait(bar(KV_FULL + bl.stage), bl.phase, abw);
+          if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u, wctx);
+          mbar_wait(bar(KV_FULL + bl.stage), bl.phase, wctx);
           if (lane == 0) ATT_EV(130);
           tc_fence_after();
         }
@@ -497,6 +512,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float c = p.scale_log2e;
     const uint32_t stg = sbase + ATT_SMEM_STG + uint32_t(warp - 4) * ATT_STG_BYTES;  // this warp's 32 x 128 B staging
     uint32_t g = 0;  // blocks processed so far by this tile
+#if ATT_SKEW_CLKS > 0
+    // One-time phase offset between the two tiles' softmax warps: left alone they run in lockstep (both in the
+    // exponential phase, then both in the ALU-bound maximum / TMEM phases), so the MUFU pipe idles ~1/3 of the time.
+    // Nothing in the pipeline re-synchronises them afterwards (S is produced a block ahead).
+    if (t == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < ATT_SKEW_CLKS) {
+      }
+    }
+#endif
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qp = item % p.n_qp;
       const int bh = item / p.n_qp;
@@ -517,19 +542,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
         const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
         const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
-        mbar_wait(bar(S_FULL + t), g & 1u, abw);
+        if (lane == 0 && qd == 2) ATT_EV(199);
+        mbar_wait(bar(S_FULL + t), g & 1u, wctx);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
+        if (lane == 0 && qd == 2) ATT_EV(300);
         float alpha = 1.0f;
         bool rescale = false;
         // P.V(j-1) of this tile must have completed before P(j) is written over P(j-1) (and before O is rescaled).
         // O_FULL cannot be lapped: its next flip needs this warp's P_FULL arrive below.
 #ifdef ATT_TRACE
-        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, abw,
+        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, &wctx,
                              turns + 4u * (t * 4 + qd), turns + 4u * ((t ^ 1) * 4 + qd),
                              AttTrace{p.trace, tr_role, &tr_n, lane == 0 && qd == 2}};
 #else
-        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, abw,
+        const SoftmaxSync sy{bar(S_EMPTY + t), bar(O_FULL + t), j > 0 ? int((g - 1) & 1u) : -1, &wctx,
                              turns + 4u * (t * 4 + qd), turns + 4u * ((t ^ 1) * 4 + qd), AttTrace{}};
 #endif
         if (warp_live) {
@@ -559,15 +586,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sy.bar_s_empty);
-          if (sy.o_parity >= 0) mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), abw);
+          if (sy.o_parity >= 0) mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), wctx);
         }
         tmem_wait_st();
+        if (lane == 0 && qd == 2) ATT_EV(320);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
         if (lane == 0 && qd == 2) ATT_EV(210 + t);
       }
-      mbar_wait(bar(O_FULL + t), (g - 1) & 1u, abw);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
+      mbar_wait(bar(O_FULL + t), (g - 1) & 1u, wctx);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
       tc_fence_after();
       if (lane == 0 && qd == 2) ATT_EV(220 + t);
       // normalise the 64 output columns of this head and hand the warp's 32 rows to one TMA store (rows >= Lq are

@@ -143,6 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0 && p.abort_word != nullptr) *reinterpret_cast<volatile unsigned int*>(p.abort_word) = 0xB200A116u;
     return;  // uniform over the CTA (and over a CTA pair: both CTAs see the same shared-memory layout)
   }
+  WaitCtx wctx = make_wait_ctx(p.abort_word);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);   // the leader's producer arrives (expect_tx covers both CTAs' bytes)
@@ -187,7 +188,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;
       const int n0 = (r % p.tiles_n) * GEMM_BN + int(cta_rank) * kBRows;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_word);
+        mbar_wait(empty_bar(stage), phase ^ 1u, wctx);
         const uint32_t sa = ring + stage * kStageBytes;
         if (elect_one()) {
           if (kCtas == 2) {
@@ -215,11 +216,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.abort_word);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, wctx);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.abort_word);
+          mbar_wait(full_bar(stage), phase, wctx);
           tc_fence_after();
           const uint32_t sa = ring + stage * kStageBytes;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
@@ -339,7 +340,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float2 st_s1 = make_float2(0.f, 0.f), st_s2 = make_float2(0.f, 0.f);
       bool released = false;
 
-      mbar_wait(tfull_bar(acc), acc_phase, p.abort_word);
+      mbar_wait(tfull_bar(acc), acc_phase, wctx);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * GEMM_BN + hf * 128 + (uint32_t(q * 32) << 16);
 

@@ -216,6 +216,35 @@ __global__ void tmem_shape_kernel(float* out, long long* cycles, int iters) {
   }
 }
 
+// MUFU rate per operand type: MODE 0 ex2.approx.ftz.f32 (8 per iteration), 1 ex2.approx.f16x2 (8 packed = 16 values),
+// 2 ex2.approx.ftz.bf16x2 (8 packed = 16 values)
+template <int MODE>
+__global__ void mufu_type_kernel(float* out, long long* cycles, int iters) {
+  uint32_t h[8];
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    x[k] = -(threadIdx.x + k) * 1e-3f;
+    h[k] = 0xB800B400u + threadIdx.x + k;  // two small negative halves
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (MODE == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+      if (MODE == 1) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[k]));
+      if (MODE == 2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[k]));
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k] + __uint_as_float(h[k] & 0x3f800000u);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 template <typename K>
 static double run(K kern, int sms, int threads, int iters, float* out, long long* cyc) {
   for (int rep = 0; rep < 2; ++rep) {
@@ -267,6 +296,13 @@ int main() {
     for (int m = 0; m < 3; ++m)
       printf("TMEM read of 128 columns x 32 lanes per warp, %-16s %d warps/SMSP: %7.1f clk per 16 KB -> %.1f B/clk/SM\n", tn[m],
              threads / 128, r[m], double(threads / 32) * 16384.0 / r[m]);
+  }
+  for (int threads : {128, 512}) {
+    const double a = run(mufu_type_kernel<0>, sms, threads, iters, out, cyc);
+    const double b = run(mufu_type_kernel<1>, sms, threads, iters, out, cyc);
+    const double c = run(mufu_type_kernel<2>, sms, threads, iters, out, cyc);
+    printf("MUFU.EX2 values per clk per SM, %d warps/SMSP: f32 %.1f   f16x2 %.1f   bf16x2 %.1f\n", threads / 128,
+           threads * 8.0 / a, threads * 16.0 / b, threads * 16.0 / c);
   }
   printf("cuda status: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

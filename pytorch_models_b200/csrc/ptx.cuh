@@ -52,6 +52,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Probe that may stay suspended in hardware for up to `hint_ns` nanoseconds before it reports "not yet".
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Non-blocking probe (no hardware suspend): has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -64,13 +76,15 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait. A protocol slip (or a fault in another role) must not hang the GPU: after B200_WAIT_LIMIT_NS of
-// polling the waiter raises the library's abort word (mapped host memory, see host_util.cu) and carries on; every
-// other wait of every CTA then falls through once it sees the word, so the kernel drains in bounded time with
-// garbage results, and the next C-ABI call returns an error instead of enqueueing more work. `abort_word` == nullptr
-// (stand-alone tools) waits forever like a plain spin.
-// The abort word lives across PCIe: it is looked at only by waits that have already lasted B200_WAIT_WATCH_NS — far
-// longer than any wait of a healthy kernel (microseconds) — so the normal path is mbarrier.try_wait and nothing else.
+// Bounded wait. A protocol slip (or a fault in another role) must not hang the GPU: a wait that has lasted
+// B200_WAIT_LIMIT_NS raises the library's abort word (mapped host memory, see host_util.cu) and returns; once the word
+// is set, every wait that has lasted B200_WAIT_WATCH_NS (far longer than any wait of a healthy kernel, which are
+// microseconds) sees it and falls through, so the kernel drains in bounded time with garbage results and the next
+// C-ABI call returns an error instead of enqueueing more work.
+// mbarrier.try_wait comes back "not yet" long before any useful time limit (a wait of a few hundred clocks already
+// takes several probes), so the probe loop is hot: it is 16 back-to-back probes — exactly the instructions of a plain
+// spin — and only every 16th failed probe pays for a counter, every 1024th for a timer read. Round-2 A/B on the
+// attention kernel: a counter or a memory read per probe costs 5-7 %; this form measures the same as the plain spin.
 #ifndef B200_WAIT_LIMIT_NS
 #define B200_WAIT_LIMIT_NS 4000000000ull
 #endif
@@ -82,25 +96,48 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* abort_word) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
+// Plain spin, for the one role whose register budget is too tight for the bounded form (the attention kernel's MMA
+// issuer, 88 registers after setmaxnreg): everything it waits on is produced by roles that ARE bounded and that keep
+// walking the protocol after giving up, so its waits still complete.
+__device__ __forceinline__ void mbar_wait_plain(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0u && abort_word != nullptr) {  // every 1024 failed probes (each suspends in hardware)
+  }
+}
+struct WaitCtx {
+  unsigned int* abort_word;  // may be nullptr (stand-alone tools): then a wait never gives up
+};
+__device__ __forceinline__ WaitCtx make_wait_ctx(unsigned int* abort_word) { return WaitCtx{abort_word}; }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const WaitCtx& w) {
+  uint32_t rounds = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if ((++rounds & 63u) == 0u && w.abort_word != nullptr) {  // every 1024 failed probes
       const uint64_t now = global_timer_ns();
       if (t0 == 0) {
         t0 = now;
       } else if (now - t0 > B200_WAIT_WATCH_NS) {
-        if (*reinterpret_cast<volatile unsigned int*>(abort_word) != 0u) return;
+        volatile unsigned int* aw = reinterpret_cast<volatile unsigned int*>(w.abort_word);
+        if (*aw != 0u) return;
         if (now - t0 > B200_WAIT_LIMIT_NS) {
-          *reinterpret_cast<volatile unsigned int*>(abort_word) = 0xB200DEADu;
+          *aw = 0xB200DEADu;
           __threadfence_system();
           return;
         }
       }
     }
   }
+}
+
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ---------------------------------------------------------------- clusters (CTA pairs)

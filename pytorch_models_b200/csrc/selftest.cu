@@ -463,6 +463,49 @@ static const AttnCase kAttnCases[] = {
     {"causal_l1100", 2, 2, 1100, 1100, true, true, 3.0f, 0, 0},
 };
 
+// Watchdog path: one CTA drops a barrier commit (B200ENC_ATTN_DEBUG_FAULT); the kernel must still terminate (within the
+// wait limit, 4 s), the status word must be raised, every entry point must refuse work until it is acknowledged, and a
+// normal launch afterwards must be correct again.
+static bool run_attn_fault() {
+  printf("attention fault injection: dropped S_FULL commit in CTA 0\n");
+  fflush(stdout);
+  const int B = 4, H = 2, L = 300, D = H * 64;
+  auto hq = rand_bf16(size_t(B) * L * 3 * D, 1.0f, false);
+  DevBuf dq(hq.size() * 2), dout(size_t(B) * L * D * 2);
+  CK(cudaMemcpy(dq.p, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice));
+  uint16_t* base = (uint16_t*)dq.p;
+  auto call = [&](int flags) {
+    return b200enc_attention(dq.p, (long long)L * 3 * D, 3 * D, base + D, base + 2 * D, (long long)L * 3 * D, 3 * D, dout.p,
+                             (long long)L * D, D, B, H, L, L, 64, 0.125f, flags, nullptr);
+  };
+  if (b200enc_async_status(0) != 0) {
+    printf("  [FAIL] status word already set\n");
+    return false;
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  int rc = call(B200ENC_ATTN_DEBUG_FAULT);
+  CK(cudaEventRecord(e1));
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const unsigned st = b200enc_async_status(0);
+  printf("  faulty launch: rc=%d sync=%s %.0f ms, status word 0x%08x\n", rc, cudaGetErrorString(e), ms, st);
+  bool ok = rc == 0 && e == cudaSuccess && st != 0 && ms > 1000.f && ms < 20000.f;
+  rc = call(0);
+  printf("  next call while the word is set: rc=%d (%s)\n", rc, b200enc_last_error());
+  ok = ok && rc == -3;
+  b200enc_async_status(1);
+  rc = call(0);
+  e = cudaDeviceSynchronize();
+  printf("  after acknowledging: rc=%d sync=%s status 0x%08x\n", rc, cudaGetErrorString(e), b200enc_async_status(0));
+  ok = ok && rc == 0 && e == cudaSuccess && b200enc_async_status(0) == 0;
+  printf("  [%s] watchdog\n", ok ? "ok" : "FAIL");
+  return ok;
+}
+
 #ifdef ATT_TRACE
 extern "C" void b200enc_debug_attention_trace(long long* buf);
 static void run_attn_trace(int B, int H, int L) {
@@ -631,6 +674,10 @@ int main(int argc, char** argv) {
       found = true;
       ok = run_attn(c) && ok;
     }
+  }
+  if (which == "attn:fault") {
+    found = true;
+    ok = run_attn_fault() && ok;
   }
 #ifdef ATT_TRACE
   if (which == "attn:trace") {

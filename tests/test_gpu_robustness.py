@@ -88,10 +88,10 @@ def test_cross_attention_layer_without_memory(pre_norm):
     sd = oracle_torch.randomize_(dec.state_dict(), 9)
     x = torch.randn(3, 70, 128)
     with torch.no_grad():
-        want = oracle_torch.decoder(sd, x, None, 2, pre_norm, 1e-5)
+        want = oracle_torch.decoder(sd, x, None, 2, pre_norm, 1e-5, prefix="")  # Decoder is an nn.ModuleList: keys "0.sa..."
         got = dec.cuda()(x.cuda()).float().cpu()
         one = dec[0](x.cuda()).float().cpu()
-        want_one = oracle_torch.decoder_layer(sd, "layers.0.", x, None, 2, pre_norm, 1e-5)
+        want_one = oracle_torch.decoder_layer(sd, "0.", x, None, 2, pre_norm, 1e-5)
     for g, w in ((got, want), (one, want_one)):
         max_abs, min_cos = error_stats(g.numpy(), w.numpy())
         assert max_abs <= 0.08 and min_cos >= 0.9999, (max_abs, min_cos)
