@@ -40,8 +40,10 @@ void b200enc_tensor_map_cache_stats(unsigned long long* hits, unsigned long long
 #define B200ENC_LINEAR_GELU_TANH 2     /* tanh GELU after bias: nn.GELU(approximate="tanh"), transformer.py:62 (no residual) */
 #define B200ENC_LINEAR_RELU 4          /* nn.ReLU, transformer.py:63 (no residual) */
 #define B200ENC_LINEAR_SILU 8          /* nn.SiLU, transformer.py:64 (no residual) */
+#define B200ENC_LINEAR_FP8 16           /* OPTIONAL variant, never the default: x and w are e4m3 bytes, see acc_scale below */
 #define B200ENC_LINEAR_DIRECT_STORE 256 /* debug: per-thread st.global epilogue without the smem transpose */
 #define B200ENC_LINEAR_ONE_CTA 512      /* debug: 128-row tiles on single CTAs instead of 256-row tiles on CTA pairs */
+#define B200ENC_LINEAR_TWO_CTA 1024     /* debug: CTA pairs even where the wave-quantisation model prefers 128-row tiles */
 
 /*
  * out[b][m][n] = epi( sum_k x[b][m][k] * w[n][k] )   for b < batches, m < M, n < N      (tcgen05 GEMM)
@@ -89,6 +91,11 @@ typedef struct b200enc_linear_args {
   int stats_rows_per_batch;    /* 0 = M. Otherwise row (b, m) of stats_out lives at b*stats_rows_per_batch +            */
   int stats_row_offset;        /* stats_row_offset + m: lets the patch-embedding GEMM, which writes tokens 1.. of every */
                                /* image, put its statistics where the first encoder layer looks for them               */
+  const float* acc_scale;      /* B200ENC_LINEAR_FP8 only: DEVICE pointer to one fp32, the product of the per-tensor   */
+                               /* dequantisation scales of x and w: out = epi(acc_scale * sum_k x8*w8 + bias ...).     */
+                               /* The FP8 variant (SURVEY §8 f rank 4) has no counterpart in the reference (its linears */
+                               /* are nn.Linear in the module's dtype, transformer.py:28-31,59,66); it exists as an    */
+                               /* opt-in with its own tolerance: K % 16 == 0, no LayerNorm fold, no statistics output. */
 } b200enc_linear_args;
 
 int b200enc_linear(const b200enc_linear_args* args, void* stream);

@@ -17,6 +17,7 @@ LINEAR_GELU_TANH = 2
 LINEAR_RELU = 4
 LINEAR_SILU = 8
 ATTN_CAUSAL = 1
+LINEAR_FP8 = 16
 LINEAR_DIRECT_STORE = 256
 DTYPE_BF16 = 0
 DTYPE_F32 = 1
@@ -38,6 +39,7 @@ class LinearArgs(ctypes.Structure):
         ("batches", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
         ("flags", c_int),
         ("stats_rows_per_batch", c_int), ("stats_row_offset", c_int),
+        ("acc_scale", c_void_p),
     ]
 
 

@@ -7,10 +7,10 @@ using namespace b200;
 
 namespace {
 
-template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats>
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats, bool kF8 = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats>;
+  auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats, kF8>;
   constexpr int kSmem = GemmSmem<kCtas, kRes>::kBytes;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), kSmem)) return rc;
   cudaLaunchConfig_t cfg = {};
@@ -40,6 +40,16 @@ int dispatch_store(bool tma, bool stats, const CUtensorMap& ta, const CUtensorMa
     if (!tma) return launch_gemm<1, kFold, kAct, kRes, false, false>(ta, tb, tc, p, grid, s);
   }
   return launch_gemm<kCtas, kFold, kAct, kRes, true, false>(ta, tb, tc, p, grid, s);
+}
+
+// The FP8 variant: bias [+ erf-GELU] [+ residual], TMA store
+template <int kCtas>
+int dispatch_fp8(bool gelu, bool res, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                 int grid, cudaStream_t s) {
+  if (gelu && res) return set_error(-1, "b200enc_linear: FP8 variant: GELU and residual cannot be combined");
+  if (gelu) return launch_gemm<kCtas, false, 1, false, true, false, true>(ta, tb, tc, p, grid, s);
+  if (res) return launch_gemm<kCtas, false, 0, true, true, false, true>(ta, tb, tc, p, grid, s);
+  return launch_gemm<kCtas, false, 0, false, true, false, true>(ta, tb, tc, p, grid, s);
 }
 
 template <int kCtas>
@@ -74,6 +84,16 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   B200_CHECK_ARG(batches >= 1 && M >= 1 && N >= 1 && K >= 1, "b200enc_linear: bad shape batches=%d M=%d N=%d K=%d",
                  batches, M, N, K);
   B200_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "b200enc_linear: K=%d and N=%d must be multiples of 8", K, N);
+  const bool fp8 = (a->flags & B200ENC_LINEAR_FP8) != 0;
+  if (fp8) {
+    B200_CHECK_ARG(K % 16 == 0 && a->ldx % 16 == 0 && a->ldw % 16 == 0 && a->x_batch_stride % 16 == 0,
+                   "b200enc_linear: FP8 variant needs K, ldx, ldw and the batch stride to be multiples of 16 bytes");
+    B200_CHECK_ARG(a->acc_scale != nullptr && a->colsum == nullptr && a->stats_out == nullptr,
+                   "b200enc_linear: FP8 variant needs acc_scale and supports neither the LayerNorm fold nor stats_out");
+    B200_CHECK_ARG((a->flags & (B200ENC_LINEAR_GELU_TANH | B200ENC_LINEAR_RELU | B200ENC_LINEAR_SILU |
+                                B200ENC_LINEAR_DIRECT_STORE)) == 0,
+                   "b200enc_linear: FP8 variant supports bias, erf-GELU and residual epilogues only");
+  }
   // ldx < K is allowed on purpose: overlapping rows express a strided 1-D convolution as a GEMM (whisper stem).
   B200_CHECK_ARG(a->ldx >= 8 && a->ldw >= K && a->ldo >= N,
                  "b200enc_linear: leading dimension smaller than the row length");
@@ -102,15 +122,39 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const bool tma_store = (a->flags & B200ENC_LINEAR_DIRECT_STORE) == 0;
   const bool stats = a->stats_out != nullptr;
 
-  // CTA pairs (256-row tiles) unless the problem has at most one 128-row tile per batch or the caller forbids it
+  // CTA pairs (256-row tiles) unless the problem has at most one 128-row tile per batch or the caller forbids it — or
+  // unless wave quantisation says otherwise (SURVEY §7 hard part 3): the kernel is persistent, so its time is
+  // ceil(tiles / slots) tile-times. At the strong-scaled ViT-B/16 shard (M = 25 216 = 98.5 x 256) the N = 768 GEMMs
+  // have 99 x 3 = 297 pair-tiles on 74 pairs = 4.01 -> 5 waves, the last one a single tile (20 % lost), while
+  // 128-row tiles give 197 x 3 = 591 tiles on 148 CTAs = 3.99 -> 4 waves. A 128-row tile costs about 1.15x half a
+  // pair-tile (3-stage ring, no operand sharing: round-1 A/B), which the model below charges.
   const bool direct = (a->flags & B200ENC_LINEAR_DIRECT_STORE) != 0;
-  const int ctas = (M > GEMM_BM && !(a->flags & B200ENC_LINEAR_ONE_CTA) && !direct) ? 2 : 1;
+  int ctas = (M > GEMM_BM && !(a->flags & B200ENC_LINEAR_ONE_CTA) && !direct) ? 2 : 1;
+  // (Measured at M = 25 216, round 2: out_proj 0.036 vs 0.037 ms in favour of 128-row tiles, FC2 (K = 3072) 0.101 vs
+  // 0.099 ms in favour of pairs — the longer main loop amortises the lone tile of the last wave — so the switch is
+  // limited to K <= 1024.)
+  if (ctas == 2 && K <= 1024 && !(a->flags & B200ENC_LINEAR_TWO_CTA)) {
+    const long long tn = (N + GEMM_BN - 1) / GEMM_BN;
+    const long long t2 = (long long)((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tn * batches;
+    const long long t1 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * tn * batches;
+    const long long s2 = sm_count() / 2, s1 = sm_count();
+    const double cost2 = double((t2 + s2 - 1) / s2);            // in pair-tile times
+    const double cost1 = double((t1 + s1 - 1) / s1) * 1.15;     // a wave of 128-row tiles covers the same area
+    if (cost1 < cost2 * 0.97) ctas = 1;
+  }
   CUtensorMap ta, tb, tc;
   int rc;
-  if ((rc = make_tmap_bf16(&ta, a->x, K, M, batches, a->ldx, batches > 1 ? a->x_batch_stride : (long long)M * a->ldx,
-                           GEMM_BK, GEMM_BM, 128)))
-    return rc;
-  if ((rc = make_tmap_bf16(&tb, a->w, K, N, 0, a->ldw, 0, GEMM_BK, GEMM_BN / ctas, 128))) return rc;
+  if (fp8) {  // 1-byte elements: the 128-byte swizzled stage row holds 128 of them
+    if ((rc = make_tmap_u8(&ta, a->x, K, M, batches, a->ldx, batches > 1 ? a->x_batch_stride : (long long)M * a->ldx,
+                           2 * GEMM_BK, GEMM_BM, 128)))
+      return rc;
+    if ((rc = make_tmap_u8(&tb, a->w, K, N, 0, a->ldw, 0, 2 * GEMM_BK, GEMM_BN / ctas, 128))) return rc;
+  } else {
+    if ((rc = make_tmap_bf16(&ta, a->x, K, M, batches, a->ldx, batches > 1 ? a->x_batch_stride : (long long)M * a->ldx,
+                             GEMM_BK, GEMM_BM, 128)))
+      return rc;
+    if ((rc = make_tmap_bf16(&tb, a->w, K, N, 0, a->ldw, 0, GEMM_BK, GEMM_BN / ctas, 128))) return rc;
+  }
   if ((rc = make_tmap_bf16(&tc, a->out, N, M, batches, a->ldo,
                            batches > 1 ? a->out_batch_stride : (long long)M * a->ldo, 64, 32, 128)))
     return rc;
@@ -143,6 +187,7 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_batch_stride = a->out_batch_stride;
   p.ldo = a->ldo;
+  p.acc_scale = a->acc_scale;
   p.debug = (a->flags >> 16) & 3;
   p.abort_word = abort_word();
 
@@ -150,6 +195,10 @@ extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   const int slots = sm_count() / ctas;  // CTAs (or CTA pairs) resident at once: the kernel is persistent
   const int grid = int(total < slots ? total : slots) * ctas;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (fp8) {
+    if (ctas == 2) return dispatch_fp8<2>(gelu, res, ta, tb, tc, p, grid, s);
+    return dispatch_fp8<1>(gelu, res, ta, tb, tc, p, grid, s);
+  }
   const int sel = (silu ? 32 : 0) | (relu ? 16 : 0) | (gelu_tanh ? 8 : 0) | (fold ? 4 : 0) | (gelu ? 2 : 0) | (res ? 1 : 0);
   if (ctas == 2) return dispatch_epilogue<2>(sel, tma_store, stats, ta, tb, tc, p, grid, s);
   return dispatch_epilogue<1>(sel, tma_store, stats, ta, tb, tc, p, grid, s);

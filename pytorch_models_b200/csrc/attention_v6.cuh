@@ -192,14 +192,11 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
   tmem_ld32(tS, v[0]);
   if (1 < n_chunks) tmem_ld32(tS + 32, v[1]);
   tmem_wait_ld();
-  ATT_TR(sy.tr, 301);
   if (2 < n_chunks) tmem_ld32(tS + 64, v[2]);
   if (3 < n_chunks) tmem_ld32(tS + 96, v[3]);
   prep_max(0);
   if (1 < n_chunks) prep_max(1);
-  ATT_TR(sy.tr, 302);
   tmem_wait_ld();
-  ATT_TR(sy.tr, 303);
   tc_fence_before();
   __syncwarp();
   if (lane_id() == 0) mbar_arrive(sy.bar_s_empty);
@@ -208,7 +205,6 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
   if (3 < n_chunks) prep_max(3);
   if (kBias) c = 1.0f;
   const float m_new = fmaxf(m, fmaxf(mx0, mx1));
-  ATT_TR(sy.tr, 304);
   // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
   // the first block with a visible key, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
@@ -251,14 +247,10 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
       if (ch == 0 && sy.o_parity >= 0) {
         // P.V of the previous block has finished: P's columns are free and O is complete. It was issued a whole
         // block ago; the wait sits here, after the first chunk's exponentials, so that its latency is covered.
-        ATT_TR(sy.tr, 305);
-        mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), *sy.wait);
-        ATT_TR(sy.tr, 306);
-        tc_fence_after();
-        ATT_TR(sy.tr, 307);
-      }
+              mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), *sy.wait);
+              tc_fence_after();
+            }
       tmem_st16(tP + ch * 16, pk);
-      ATT_TR(sy.tr, 310 + ch);
     }
   }
 #if ATT_TURN_SPINS > 0
@@ -542,11 +534,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
         const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
         const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
-        if (lane == 0 && qd == 2) ATT_EV(199);
         mbar_wait(bar(S_FULL + t), g & 1u, wctx);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
-        if (lane == 0 && qd == 2) ATT_EV(300);
         float alpha = 1.0f;
         bool rescale = false;
         // P.V(j-1) of this tile must have completed before P(j) is written over P(j-1) (and before O is rescaled).
@@ -589,7 +579,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (sy.o_parity >= 0) mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), wctx);
         }
         tmem_wait_st();
-        if (lane == 0 && qd == 2) ATT_EV(320);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));

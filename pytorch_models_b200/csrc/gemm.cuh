@@ -72,6 +72,7 @@ struct GemmParams {
   __nv_bfloat16* out;          // used by the direct-store path only
   long long out_batch_stride;
   int ldo;
+  const float* acc_scale;  // kF8 only: device scalar, dequantisation scale of the accumulator
   int debug;  // timing experiments only: bit0 = skip the output store, bit1 = skip the whole epilogue body
   unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
 };
@@ -112,7 +113,10 @@ __device__ __forceinline__ float2 silu_fast2(float2 x) {
 }
 
 // kAct: 0 = none, 1 = erf-GELU, 2 = tanh-GELU, 3 = ReLU, 4 = SiLU
-template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats>
+// kF8: operands are e4m3 bytes (the optional FP8 variant, b200enc.h B200ENC_LINEAR_FP8): a stage still holds 128-byte
+// rows, i.e. 128 instead of 64 K elements, each tcgen05.mma (kind::f8f6f4) consumes K = 32, and the accumulator is
+// multiplied by *p.acc_scale (the product of the two per-tensor dequantisation scales) before the bias is added.
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats, bool kF8 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -172,7 +176,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  constexpr int kBKe = kF8 ? 2 * GEMM_BK : GEMM_BK;  // K elements per 128-byte stage row
+  const int num_kb = (p.K + kBKe - 1) / kBKe;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batches;
   const int first_tile = blockIdx.x / kCtas;  // both CTAs of a pair walk the same tile sequence
@@ -195,12 +200,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
             const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
-            tma_load_3d_2cta(&tmA, leader_full, sa, kb * GEMM_BK, m0, b);
-            tma_load_2d_2cta(&tmB, leader_full, sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
+            tma_load_3d_2cta(&tmA, leader_full, sa, kb * kBKe, m0, b);
+            tma_load_2d_2cta(&tmB, leader_full, sa + GEMM_A_BYTES, kb * kBKe, n0);
           } else {
             mbar_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_3d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0, b);
-            tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * GEMM_BK, n0);
+            tma_load_3d(&tmA, full_bar(stage), sa, kb * kBKe, m0, b);
+            tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * kBKe, n0);
           }
         }
         __syncwarp();
@@ -213,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only; converged warp)
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
+      constexpr uint32_t idesc = kF8 ? make_idesc_e4m3(kTileM, GEMM_BN) : make_idesc_bf16(kTileM, GEMM_BN, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, wctx);
@@ -228,8 +233,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
-              // advancing K by 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              if (kCtas == 2)
+              // advancing K by 16 bf16 (32 e4m3) = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              if (kF8) {
+                if (kCtas == 2)
+                  umma_ss_f8_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else
+                  umma_ss_f8(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              } else if (kCtas == 2)
                 umma_ss_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
               else
                 umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -336,6 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           nmr = -mean * rstd;
         }
       }
+      const float f8_scale = kF8 ? __ldg(p.acc_scale) : 1.0f;
       float st_shift = 0.0f;
       float2 st_s1 = make_float2(0.f, 0.f), st_s2 = make_float2(0.f, 0.f);
       bool released = false;
@@ -382,6 +393,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         uint32_t packed[32];
         const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
+        const float2 f8_scale2 = make_float2(f8_scale, f8_scale);
 #pragma unroll
         for (int j4 = 0; j4 < 16; ++j4) {
           // 4 columns per step as two fp32 pairs (packed FFMA2 pipe); column vectors are broadcast 16-byte smem loads
@@ -396,7 +408,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                          __uint_as_float(idx < 32 ? v0[idx + 1] : v1[idx + 1 - 32]));
             const float2 cb2 = u == 0 ? make_float2(cb.x, cb.y) : make_float2(cb.z, cb.w);
             const float2 cs2 = u == 0 ? make_float2(cs.x, cs.y) : make_float2(cs.z, cs.w);
-            x[u] = kFold ? __ffma2_rn(rstd2, a, __ffma2_rn(nmr2, cs2, cb2)) : __fadd2_rn(a, cb2);
+            x[u] = kFold ? __ffma2_rn(rstd2, a, __ffma2_rn(nmr2, cs2, cb2))
+                         : (kF8 ? __ffma2_rn(a, f8_scale2, cb2) : __fadd2_rn(a, cb2));
             if (kAct == 1) x[u] = gelu_erf_fast2(x[u]);
             if (kAct == 2) x[u] = gelu_tanh_fast2(x[u]);
             if (kAct == 3) x[u] = make_float2(fmaxf(x[u].x, 0.0f), fmaxf(x[u].y, 0.0f));

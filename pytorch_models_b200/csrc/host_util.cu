@@ -63,7 +63,7 @@ TmapCacheStats tmap_cache_stats() {
 }
 
 int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, int swizzle_bytes) {
+                      const uint32_t* box, int swizzle_bytes, int elem_bytes) {
   if (rank < 1 || rank > 5) return set_error(-1, "tensor map rank %d out of range", rank);
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return set_error(-1, "tensor base %p not 16-byte aligned", base);
   for (int i = 0; i + 1 < rank; ++i)
@@ -73,7 +73,7 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.w[0] = reinterpret_cast<uintptr_t>(base);
-  key.w[1] = uint64_t(rank) | (uint64_t(swizzle_bytes) << 8);
+  key.w[1] = uint64_t(rank) | (uint64_t(swizzle_bytes) << 8) | (uint64_t(elem_bytes) << 16);
   for (int i = 0; i < rank; ++i) key.w[2 + i] = dims[i];
   for (int i = 0; i + 1 < rank; ++i) key.w[7 + i] = strides_bytes[i];
   for (int i = 0; i < rank; ++i) key.w[11 + i / 2] |= uint64_t(box[i]) << (32 * (i & 1));
@@ -100,7 +100,8 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64
   if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
   if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), d, st, bx, estr,
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, cuuint32_t(rank), const_cast<void*>(base), d, st, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -133,6 +134,18 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
   const uint64_t strides[2] = {row_stride * 2, batch_stride * 2};
   const uint32_t box[3] = {box_inner, box_rows, 1};
   return make_tmap_bf16_nd(out, base, rank, dims, strides, box, swizzle_bytes);
+}
+
+int make_tmap_u8(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches, uint64_t row_stride,
+                 uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
+  if (row_stride % 16 != 0) return set_error(-1, "row stride %llu bytes is not a multiple of 16", (unsigned long long)row_stride);
+  const int rank = batches == 0 ? 2 : 3;
+  if (rank == 3 && batch_stride % 16 != 0)
+    return set_error(-1, "batch stride %llu bytes is not a multiple of 16", (unsigned long long)batch_stride);
+  const uint64_t dims[3] = {inner, rows, batches == 0 ? 1 : batches};
+  const uint64_t strides[2] = {row_stride, batch_stride};
+  const uint32_t box[3] = {box_inner, box_rows, 1};
+  return make_tmap_bf16_nd(out, base, rank, dims, strides, box, swizzle_bytes, 1);
 }
 
 // ---------------------------------------------------------------- per-device facts

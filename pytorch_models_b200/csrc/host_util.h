@@ -35,7 +35,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
 
 // General form (rank <= 5): dims / box in elements, strides[i] = byte stride of dim i+1. Same cache.
 int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, int swizzle_bytes);
+                      const uint32_t* box, int swizzle_bytes, int elem_bytes = 2);
+
+// The same 2-D / 3-D view for 1-byte elements (e4m3 operands of the optional FP8 linears); strides in elements.
+int make_tmap_u8(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches, uint64_t row_stride,
+                 uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
 
 struct TmapCacheStats {
   unsigned long long hits, misses;

@@ -169,7 +169,8 @@ static bool run_linear(const LinearCase& c) {
   CK(cudaMemset(dout.p, 0x7f, dout.bytes));  // sentinel 0x7f7f = 3.39e38 in bf16
 
   const int dbg = getenv("B200_DEBUG_FLAGS") ? atoi(getenv("B200_DEBUG_FLAGS")) : 0;  // timing experiments only
-  const int flags = (c.gelu == 1 ? B200ENC_LINEAR_GELU : c.gelu == 2 ? B200ENC_LINEAR_GELU_TANH : c.gelu == 3 ? B200ENC_LINEAR_RELU : c.gelu == 4 ? B200ENC_LINEAR_SILU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
+  const int extra_flags = getenv("B200_LINEAR_FLAGS") ? atoi(getenv("B200_LINEAR_FLAGS")) : 0;  // A/B: 512 one CTA, 1024 pairs
+  const int flags = extra_flags | (c.gelu == 1 ? B200ENC_LINEAR_GELU : c.gelu == 2 ? B200ENC_LINEAR_GELU_TANH : c.gelu == 3 ? B200ENC_LINEAR_RELU : c.gelu == 4 ? B200ENC_LINEAR_SILU : 0) | (c.direct ? B200ENC_LINEAR_DIRECT_STORE : 0) | (dbg << 16);
   const int n_slices = (N + 127) / 128;
   const bool want_stats = c.res && !c.fold && !c.direct;
   GuardedBuf gso(size_t(B) * M * n_slices * 8);

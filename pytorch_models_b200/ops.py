@@ -140,13 +140,50 @@ def linear(
     args = _lib.LinearArgs(
         x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), w.stride(0), _ptr(bias), _ptr(colsum),
         _ptr(rowstats), parts, float(ln_eps), _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1),
-        _ptr(stats_out), batches, M, N, K, flags, int(stats_rows), int(stats_row_offset),
+        _ptr(stats_out), batches, M, N, K, flags, int(stats_rows), int(stats_row_offset), None,
     )
     _call(
         "b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=colsum is not None, gelu=gelu, res=residual is not None),
         dev, ctypes.byref(args),
     )
     return out
+
+
+def linear_fp8(x8: Tensor, w8: Tensor, acc_scale: Tensor, bias: Tensor | None, out: Tensor, *, gelu: bool = False,
+               residual: Tensor | None = None) -> Tensor:
+    """OPTIONAL FP8 variant (never used unless asked for): out = epi(acc_scale * (x8 @ w8.T) + bias) with e4m3 operands.
+
+    x8: (M, K) or (batches, M, K) ``torch.float8_e4m3fn``, w8: (N, K) e4m3, acc_scale: 1-element fp32 CUDA tensor holding
+    the product of the two per-tensor dequantisation scales, bias fp32 (N) or None, out bf16. Epilogues: bias,
+    bias + erf-GELU, bias + residual. K must be a multiple of 16."""
+    dev = _need_cuda(x8, w8, acc_scale, bias, out, residual)
+    _need(x8, torch.float8_e4m3fn, "x8"), _need(w8, torch.float8_e4m3fn, "w8"), _need(out, torch.bfloat16, "out")
+    _need(acc_scale, torch.float32, "acc_scale"), _need(bias, torch.float32, "bias"), _need(residual, torch.bfloat16, "residual")
+    ret = out
+    if x8.dim() == 2:
+        x8, out = x8.unsqueeze(0), out.unsqueeze(0)
+        residual = None if residual is None else residual.unsqueeze(0)
+    batches, M, K = x8.shape
+    N = w8.shape[0]
+    if w8.shape[1] != K or out.shape != (batches, M, N) or acc_scale.numel() != 1:
+        raise ValueError(f"shape mismatch: x8 {tuple(x8.shape)}, w8 {tuple(w8.shape)}, out {tuple(out.shape)}")
+    if x8.stride(2) != 1 or w8.stride(1) != 1 or out.stride(2) != 1:
+        raise ValueError("inner strides must be 1")
+    res_bs, ldr = 0, 0
+    if residual is not None:
+        if residual.shape[-2:] != (M, N) or residual.stride(2) != 1:
+            raise ValueError(f"residual shape {tuple(residual.shape)} does not match ({M}, {N})")
+        res_bs = 0 if residual.shape[0] == 1 else residual.stride(0)
+        ldr = residual.stride(1)
+    flags = _lib.LINEAR_FP8 | (_lib.LINEAR_GELU if gelu else 0)
+    args = _lib.LinearArgs(
+        x8.data_ptr(), x8.stride(0), x8.stride(1), w8.data_ptr(), w8.stride(0), _ptr(bias), None, None, 0, 0.0,
+        _ptr(residual), res_bs, ldr, out.data_ptr(), out.stride(0), out.stride(1), None, batches, M, N, K, flags, 0, 0,
+        acc_scale.data_ptr(),
+    )
+    _call("b200enc_linear", dict(batches=batches, M=M, N=N, K=K, fold=False, gelu=gelu, res=residual is not None, fp8=True),
+          dev, ctypes.byref(args))
+    return ret
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, causal: bool = False,

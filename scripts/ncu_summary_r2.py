@@ -62,7 +62,8 @@ for rep, title in (("r2_c2_head", "C2 (ViT-B/16, batch 1024): patch rows, patch-
                    ("r2_c4_layer", "C4 (DINOv2 L/14 518, batch 128): one encoder layer"),
                    ("r2_c5_layer", "C5 (Whisper large-v3 encoder, batch 64): one encoder layer"),
                    ("r2_attn_l197", "attention kernel alone, L=197, B=1024, H=12 (selftest perf_vitb_b1024)"),
-                   ("r2_attn_l1500", "attention kernel alone, L=1500, B=64, H=20 (selftest perf_whisper_b64)")):
+                   ("r2_attn_l1500", "attention kernel alone, L=1500, B=64, H=20 (selftest perf_whisper_b64)"),
+                   ("r2_cudnn_sdpa_l1500", "LIBRARY BASELINE: cuDNN SDPA kernel, L=1500, B=64, H=20, bf16 (tests/tools/gpu_sdpa_cudnn_probe.py)")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         print("missing", path)

@@ -227,9 +227,9 @@ def test_twelve_layer_stack_trained_like(kind):
             v.mul_(0.3)  # keep the stream's statistics dominated by the input, like LayerScale-d trained nets
     x = _trained_like(4 * L, d, kind, 33).view(4, L, d).bfloat16()
     with torch.no_grad():
-        want = oracle_torch.encoder(sd, x.float(), heads, True, 1e-5)
+        want = oracle_torch.encoder(sd, x.float(), heads, True, 1e-5, prefix="")  # Encoder is an nn.Sequential: "0.sa..."
         sd_b = {k: v.cuda().bfloat16() for k, v in sd.items()}
-        lib = oracle_torch.encoder(sd_b, x.cuda(), heads, True, 1e-5).float().cpu()
+        lib = oracle_torch.encoder(sd_b, x.cuda(), heads, True, 1e-5, prefix="").float().cpu()
         got = enc.cuda()(x.cuda()).float().cpu()
     # compare what a consumer sees: the stream after a final LayerNorm (unit scale)
     ln = lambda t: F.layer_norm(t, (d,))  # noqa: E731
