@@ -102,6 +102,7 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
 /* flags for b200enc_attention */
 #define B200ENC_ATTN_CAUSAL 1 /* key j only visible to queries i >= j (is_causal=True of SDPA: DecoderLayer, transformer.py:97) */
+#define B200ENC_ATTN_GENERAL 131072 /* debug / A-B: use the streaming (online-softmax) kernel even where the short-sequence kernel applies */
 #define B200ENC_ATTN_DEBUG_FAULT 65536 /* self-test only: one CTA drops a barrier commit so that the watchdog path runs */
 
 /*
@@ -113,6 +114,8 @@ int b200enc_linear(const b200enc_linear_args* args, void* stream);
  * [B, Lq, H*64] ready for out_proj. head_dim must be 64 (every BASELINE config). Lq != Lkv is allowed
  * (the 1-query MAP pooling head, image/vit.py:41). K/V stream in blocks of 128 rows with an online
  * softmax. With B200ENC_ATTN_CAUSAL the K/V blocks above the diagonal are skipped entirely.
+ * Unmasked calls with Lkv <= 256 (ViT-B/16 at 224 px: 197 tokens) take a single-pass kernel instead: the whole score
+ * row of a query lives in tensor memory, exact maximum, no rescaling (csrc/attention_short.cuh).
  */
 int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                       long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,

@@ -4,6 +4,7 @@
 #include "attention_v6.cuh"
 #else
 #include "attention.cuh"
+#include "attention_short.cuh"
 #endif
 #include "host_util.h"
 
@@ -31,6 +32,54 @@ int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
 }
 }  // namespace
 
+#ifndef ATT_V6
+// Lkv <= 256, no mask: the single-pass kernel of attention_short.cuh. TMEM layout (see its header): private columns
+// for S and O where 512 columns allow it, otherwise O_t over the upper columns of S_t.
+static int attention_short_impl(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
+                                long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo,
+                                int B, int H, int Lq, int Lkv, float scale, int flags, void* stream) {
+  AttnShortParams p;
+  p.nk16 = (Lkv + 15) & ~15;
+  CUtensorMap tq, tk, tv, to;
+  int rc;
+  const long long qbs = B > 1 ? q_batch_stride : (long long)Lq * ldq;
+  const long long kbs = B > 1 ? kv_batch_stride : (long long)Lkv * ldkv;
+  const long long obs = B > 1 ? out_batch_stride : (long long)Lq * ldo;
+  if ((rc = make_tmap_bf16(&tq, q, uint64_t(H) * ATT_HD, Lq, B, ldq, qbs, ATT_HD, ATT_BQ, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tk, k, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, p.nk16, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tv, v, uint64_t(H) * ATT_HD, Lkv, B, ldkv, kbs, ATT_HD, p.nk16, 128))) return rc;
+  if ((rc = make_tmap_bf16(&to, out, uint64_t(H) * ATT_HD, Lq, B, ldo, obs, ATT_HD, 32, 128))) return rc;
+  p.B = B;
+  p.H = H;
+  p.Lq = Lq;
+  p.Lkv = Lkv;
+  p.n_qp = (Lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
+  p.n_items = B * H * p.n_qp;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  if (p.nk16 <= 192) {
+    p.tm_s0 = 0, p.tm_s1 = 256, p.tm_o0 = 192, p.tm_o1 = 448, p.alias0 = p.alias1 = 0;
+  } else if (p.nk16 <= 224) {
+    p.tm_s0 = 0, p.tm_s1 = 224, p.tm_o0 = 448, p.tm_o1 = 224 + 128, p.alias0 = 0, p.alias1 = 1;
+  } else {
+    p.tm_s0 = 0, p.tm_s1 = 256, p.tm_o0 = 128, p.tm_o1 = 256 + 128, p.alias0 = p.alias1 = 1;
+  }
+  p.abort_word = abort_word();
+  p.debug_fault = (flags >> 16) & 1;
+#ifdef ATT_TRACE
+  p.trace = g_attention_trace;
+#else
+  p.trace = nullptr;
+#endif
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  // the row length of ViT at 224 px (197 tokens -> 13 halves of 16 columns) has its own instantiation
+  auto kern = p.nk16 == 208 ? attention_short_kernel<13> : attention_short_kernel<0>;
+  if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), ATS_SMEM_BYTES))) return rc;
+  kern<<<grid, ATT_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, to, p);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+#endif
+
 static int attention_impl(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                           long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
                           int H, int Lq, int Lkv, int head_dim, float scale, int flags, const float* bias,
@@ -46,6 +95,11 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
                  "b200enc_attention: output rows must be 16-byte aligned");
   CUtensorMap tq, tk, tv, to;
   int rc;
+#ifndef ATT_V6
+  if (Lkv <= ATS_MAX_KV && bias == nullptr && !(flags & (B200ENC_ATTN_CAUSAL | B200ENC_ATTN_GENERAL)))
+    return attention_short_impl(q, q_batch_stride, ldq, k, v, kv_batch_stride, ldkv, out, out_batch_stride, ldo, B, H, Lq,
+                                Lkv, scale, flags, stream);
+#endif
   const long long qbs = B > 1 ? q_batch_stride : (long long)Lq * ldq;
   const long long kbs = B > 1 ? kv_batch_stride : (long long)Lkv * ldkv;
   if ((rc = make_tmap_bf16(&tq, q, uint64_t(H) * ATT_HD, Lq, B, ldq, qbs, ATT_HD, ATT_BQ, 128))) return rc;

@@ -103,6 +103,16 @@ __device__ __forceinline__ void mbar_wait_plain(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait that parks the warp in hardware: mbarrier.try_wait with an explicit suspend-time hint stays suspended until the
+// phase completes (or the hint runs out) instead of coming back after a few dozen clocks, so a waiting warp issues
+// almost nothing and leaves its sub-partition's issue slots to the warps that compute.
+#ifndef B200_WAIT_HINT_NS
+#define B200_WAIT_HINT_NS 100000u
+#endif
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait_hint(bar, parity, B200_WAIT_HINT_NS)) {
+  }
+}
 struct WaitCtx {
   unsigned int* abort_word;  // may be nullptr (stand-alone tools): then a wait never gives up
 };
@@ -377,6 +387,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {

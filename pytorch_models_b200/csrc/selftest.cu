@@ -356,10 +356,11 @@ static bool run_attn(const AttnCase& c) {
   const uint16_t* kvbase_h = c.self_qkv ? hq.data() : hkv.data();
   uint16_t* kvbase_d = (uint16_t*)(c.self_qkv ? dq.p : dkv.p);
   const float scale = 0.125f;
+  const int attn_extra_flags = getenv("B200_ATTN_FLAGS") ? atoi(getenv("B200_ATTN_FLAGS")) : 0;  // A/B: 131072 = general kernel
   auto call = [&]() {
     return b200enc_attention(dq.p, (long long)Lq * ldq, ldq, kvbase_d + koff, kvbase_d + voff, (long long)Lkv * ldkv,
                              ldkv, dout.p, (long long)Lq * D, D, B, H, Lq, Lkv, 64, scale,
-                             c.causal ? B200ENC_ATTN_CAUSAL : 0, nullptr);
+                             (c.causal ? B200ENC_ATTN_CAUSAL : 0) | attn_extra_flags, nullptr);
   };
   int rc = call();
   if (rc) {
@@ -461,6 +462,19 @@ static const AttnCase kAttnCases[] = {
     {"perf_dinov2_b128", 128, 16, 1370, 1370, true, false, 1.0f, 1, 5},
     {"perf_whisper_b64", 64, 20, 1500, 1500, true, false, 1.0f, 1, 5},
     {"l1500_wide", 1, 3, 1500, 1500, true, false, 4.0f, 0, 0},
+    // short-sequence kernel (attention_short.cuh): every TMEM layout (nk16 <= 192, <= 224, <= 256), ragged tails
+    {"l192", 2, 2, 192, 192, true, false, 2.0f, 0, 0},
+    {"l193", 2, 2, 193, 193, true, false, 2.0f, 0, 0},
+    {"l208", 2, 2, 208, 208, true, false, 2.0f, 0, 0},
+    {"l224", 2, 2, 224, 224, true, false, 2.0f, 0, 0},
+    {"l225", 2, 2, 225, 225, true, false, 2.0f, 0, 0},
+    {"l250", 3, 2, 250, 250, true, false, 2.0f, 0, 0},
+    {"l1", 3, 2, 1, 1, true, false, 2.0f, 0, 0},
+    {"l33", 3, 2, 33, 33, true, false, 2.0f, 0, 0},
+    {"cross_q600_kv250", 2, 2, 600, 250, false, false, 2.0f, 0, 0},
+    {"cross_q700_kv100", 2, 2, 700, 100, false, false, 2.0f, 0, 0},
+    {"many_short_items", 300, 6, 197, 197, true, false, 3.0f, 30, 0},
+    {"many_short_q300", 200, 2, 300, 200, false, false, 2.0f, 20, 0},
     {"causal_l1100", 2, 2, 1100, 1100, true, true, 3.0f, 0, 0},
 };
 
