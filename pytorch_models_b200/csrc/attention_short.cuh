@@ -30,6 +30,9 @@
 
 namespace b200 {
 
+#ifndef ATS_SPLIT_QK
+#define ATS_SPLIT_QK 0
+#endif
 #ifndef ATS_PARKED_WAITS
 #define ATS_PARKED_WAITS 1
 #endif
@@ -165,9 +168,23 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint64_t dk = make_smem_desc_sw128(st + ATS_OFF_K, 16, 1024);
       const bool drop_commit = p.debug_fault == 1 && blockIdx.x == 0 && n == 0 && t == 0;
       if (elect_one()) {
+#if ATS_SPLIT_QK
+        if (p.nk16 > 128) {  // two column groups: [0,128) and [128,nk16)
+          const uint32_t idesc_a = make_idesc_bf16(ATT_BQ, 128, 0, 0);
+          const uint32_t idesc_b = make_idesc_bf16(ATT_BQ, p.nk16 - 128, 0, 0);
 #pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k)
-          umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1), dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1), dq + 2u * k, dk + 2u * k, idesc_a, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1) + 128, dq + 2u * k, dk + 1024u + 2u * k, idesc_b, k != 0 ? 1u : 0u);
+        } else
+#endif
+        {
+#pragma unroll
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1), dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        }
         if (!drop_commit) umma_commit(bar(S_FULL + t));
       }
       __syncwarp();
