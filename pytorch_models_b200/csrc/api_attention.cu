@@ -56,12 +56,14 @@ static int attention_short_impl(const void* q, long long q_batch_stride, int ldq
   p.n_qp = (Lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
   p.n_items = B * H * p.n_qp;
   p.scale_log2e = scale * 1.4426950408889634f;
-  if (p.nk16 <= 192) {
-    p.tm_s0 = 0, p.tm_s1 = 256, p.tm_o0 = 192, p.tm_o1 = 448, p.alias0 = p.alias1 = 0;
-  } else if (p.nk16 <= 224) {
-    p.tm_s0 = 0, p.tm_s1 = 224, p.tm_o0 = 448, p.tm_o1 = 224 + 128, p.alias0 = 0, p.alias1 = 1;
-  } else {
-    p.tm_s0 = 0, p.tm_s1 = 256, p.tm_o0 = 128, p.tm_o1 = 256 + 128, p.alias0 = p.alias1 = 1;
+  if (p.nk16 <= 176) {  // everything has its own columns: S_t 176 | O_t 64 | l_t 16
+    p.tm_s0 = 0, p.tm_o0 = 176, p.tm_l0 = 240, p.tm_s1 = 256, p.tm_o1 = 432, p.tm_l1 = 496, p.alias0 = p.alias1 = 0;
+  } else if (p.nk16 <= 208) {  // S0 208 | l0 16 | S1 208 | l1 16 | O0 64; O1 over the upper columns of S1
+    p.tm_s0 = 0, p.tm_l0 = 208, p.tm_s1 = 224, p.tm_l1 = 432, p.tm_o0 = 448, p.tm_o1 = 224 + 128, p.alias0 = 0, p.alias1 = 1;
+  } else if (p.nk16 <= 240) {  // both O_t over S_t; l_t behind the scores
+    p.tm_s0 = 0, p.tm_o0 = 128, p.tm_l0 = 240, p.tm_s1 = 256, p.tm_o1 = 256 + 128, p.tm_l1 = 496, p.alias0 = p.alias1 = 1;
+  } else {  // the scores fill all 256 columns of a tile: O_t and l_t both lie over them
+    p.tm_s0 = 0, p.tm_o0 = 128, p.tm_l0 = 192, p.tm_s1 = 256, p.tm_o1 = 256 + 128, p.tm_l1 = 256 + 192, p.alias0 = p.alias1 = 1;
   }
   p.abort_word = abort_word();
   p.debug_fault = (flags >> 16) & 1;

@@ -30,9 +30,6 @@
 
 namespace b200 {
 
-#ifndef ATS_SPLIT_QK
-#define ATS_SPLIT_QK 0
-#endif
 #ifndef ATS_PARKED_WAITS
 #define ATS_PARKED_WAITS 1
 #endif
@@ -48,7 +45,8 @@ constexpr int ATS_STAGE_BYTES = 2 * ATT_TILE_BYTES + 2 * ATS_KV_BYTES;  // Q0 | 
 constexpr int ATS_OFF_K = 2 * ATT_TILE_BYTES;
 constexpr int ATS_OFF_V = ATS_OFF_K + ATS_KV_BYTES;
 constexpr int ATS_SMEM_STG = 2 * ATS_STAGE_BYTES;                       // 8 warps x 4 KB output staging
-constexpr int ATS_SMEM_BAR = ATS_SMEM_STG + 8 * ATT_STG_BYTES;
+constexpr int ATS_SMEM_ONES = ATS_SMEM_STG + 8 * ATT_STG_BYTES;  // 16 rows x 128 B of bf16 1.0: B operand of the row-sum MMA
+constexpr int ATS_SMEM_BAR = ATS_SMEM_ONES + 2048;
 constexpr int ATS_SMEM_BYTES = ATS_SMEM_BAR + 256;
 static_assert(ATS_SMEM_BYTES <= 232448, "short attention kernel: shared memory budget");
 
@@ -58,6 +56,7 @@ struct AttnShortParams {
   int n_qp, n_items;  // as AttnParams
   float scale_log2e;
   int tm_s0, tm_s1, tm_o0, tm_o1;  // TMEM columns of S_t (P_t in place) and O_t
+  int tm_l0, tm_l1;                // 16 TMEM columns per tile that receive the row sums l = P . 1 (all 16 equal)
   int alias0, alias1;              // 1: O_t overlaps S_t, the next score MMA of the tile waits for the epilogue's read of O_t
   unsigned int* abort_word;
   int debug_fault;
@@ -115,6 +114,8 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
   }
+  for (int i = threadIdx.x; i < 2048 / 4; i += ATT_THREADS) reinterpret_cast<uint32_t*>(smem + ATS_SMEM_ONES)[i] = 0x3f803f80u;
+  fence_proxy_async_smem();  // the tensor core reads the tile through the async proxy
   if (warp == 1) {
     tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     tmem_relinquish();
@@ -157,6 +158,8 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     uint32_t done = 0;
     const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, p.nk16, 0, 0);
     const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
+    const uint32_t idesc_l = make_idesc_bf16(ATT_BQ, 16, 0, 0);
+    const uint64_t d_ones = make_smem_desc_sw128(sbase + ATS_SMEM_ONES, 16, 1024);
     const int ksteps = p.nk16 >> 4;
     auto issue_qk = [&](int n, int t) {
       const uint32_t st = sbase + (uint32_t(n) & 1u) * ATS_STAGE_BYTES;
@@ -168,18 +171,6 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint64_t dk = make_smem_desc_sw128(st + ATS_OFF_K, 16, 1024);
       const bool drop_commit = p.debug_fault == 1 && blockIdx.x == 0 && n == 0 && t == 0;
       if (elect_one()) {
-#if ATS_SPLIT_QK
-        if (p.nk16 > 128) {  // two column groups: [0,128) and [128,nk16)
-          const uint32_t idesc_a = make_idesc_bf16(ATT_BQ, 128, 0, 0);
-          const uint32_t idesc_b = make_idesc_bf16(ATT_BQ, p.nk16 - 128, 0, 0);
-#pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1), dq + 2u * k, dk + 2u * k, idesc_a, k != 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1) + 128, dq + 2u * k, dk + 1024u + 2u * k, idesc_b, k != 0 ? 1u : 0u);
-        } else
-#endif
         {
 #pragma unroll
           for (int k = 0; k < ATT_HD / 16; ++k)
@@ -203,6 +194,11 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int k = 0; k < ATS_MAX_KV / 16; ++k)
           if (k < ksteps) umma_ts(d_o, pa0 + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : 0u);
+        // l_t = P_t . 1: the row sums of the bf16 probabilities the tensor core actually multiplies with, for the price
+        // of nk16/16 MMAs of N = 16 (8 clocks each) instead of 128 FADD2 per softmax thread
+#pragma unroll
+        for (int k = 0; k < ATS_MAX_KV / 16; ++k)
+          if (k < ksteps) umma_ts(tmem_base + (t == 0 ? p.tm_l0 : p.tm_l1), pa0 + 8u * k, d_ones + 2u * (k & 3), idesc_l, k != 0 ? 1u : 0u);
         umma_commit(bar(O_FULL + t));
       }
       __syncwarp();
@@ -266,6 +262,7 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t lane_off = uint32_t(qd * 32) << 16;
     const uint32_t tS = tmem_base + uint32_t(t == 0 ? p.tm_s0 : p.tm_s1) + lane_off;
     const uint32_t tO = tmem_base + uint32_t(t == 0 ? p.tm_o0 : p.tm_o1) + lane_off;
+    const uint32_t tL = tmem_base + uint32_t(t == 0 ? p.tm_l0 : p.tm_l1) + lane_off;
     const float c = p.scale_log2e;
     const int nkv = p.Lkv;
     const int nh = kNH > 0 ? kNH : (p.nk16 >> 4);  // 16-column halves of the score row (compile-time for kNH > 0)
@@ -285,7 +282,6 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       ATS_WAIT(bar(S_FULL + t), g & 1u);
       if (lane == 0 && qd == 0) ATT_EV(200 + t);
       tc_fence_after();
-      float l = 1.0f;
       if (warp_live) {
         uint32_t v0[32], v1[32], v2[32], v3[32];
         // ---- pass 1: exact row maximum. Chunks 4..7 first, then chunks 0..3 — which stay in registers for pass 2.
@@ -350,7 +346,6 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // ---- pass 2: exponentials, row sum, P over S. Chunks 0..3 come out of the registers of pass 1 (already
         // masked); each array is refilled with chunk 4..7 as soon as its chunk is done, so those loads hide behind
         // the exponentials.
-        float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
         auto exp_chunk = [&](uint32_t(&v)[32], int ch, bool remask) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -367,7 +362,6 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #else
                 const float2 pr = make_float2(fast_exp2(e.x), fast_exp2(e.y));
 #endif
-                if (i & 1) sum1 = __fadd2_rn(sum1, pr); else sum0 = __fadd2_rn(sum0, pr);
                 pk[i] = pack_bf16x2(pr.x, pr.y);
               }
               tmem_st8(tS + ch * 16 + hf * 8, pk);
@@ -389,8 +383,6 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           if (6 < n_ch) exp_chunk(v2, 6, true);
           if (7 < n_ch) exp_chunk(v3, 7, true);
         }
-        const float2 sum = __fadd2_rn(sum0, sum1);
-        l = sum.x + sum.y;
         tmem_wait_st();
       }
       tc_fence_before();
@@ -404,6 +396,7 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         uint32_t o0[32], o1[32];
         tmem_ld32(tO, o0);
         tmem_ld32(tO + 32, o1);
+        const uint32_t lsum = tmem_ld1(tL);
         if (elect_one()) tma_store_wait_read<0>();  // the previous item's store has finished reading the staging
         __syncwarp();
         tmem_wait_ld();
@@ -412,7 +405,7 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(T_FREE + t));
         }
-        const float inv = 1.0f / l;
+        const float inv = 1.0f / __uint_as_float(lsum);
         uint8_t* dst = smem + ATS_SMEM_STG + (warp - 4) * ATT_STG_BYTES + lane * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

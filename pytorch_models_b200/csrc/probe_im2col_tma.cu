@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 #include "ptx.cuh"
 using namespace b200;
@@ -17,7 +18,7 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint32_t bar, 
       : "memory");
 }
 
-__global__ void probe(const __grid_constant__ CUtensorMap tm, uint16_t* out, int i0, int ph0, int nc, int rows, int bytes) {
+__global__ void probe(const __grid_constant__ CUtensorMap tm, uint16_t* out, int i0, int ph0, int nc, int rows, int bytes, int swz) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem), b = sb + 16384;
   if (sb & 1023u) {
@@ -36,12 +37,14 @@ __global__ void probe(const __grid_constant__ CUtensorMap tm, uint16_t* out, int
   mbar_wait_plain(b, 0);
   for (int idx = threadIdx.x; idx < rows * 64; idx += blockDim.x) {
     const int r = idx / 64, e = idx % 64;
-    const int chunk = (e / 8) ^ (r & 7);  // undo the 128B swizzle
+    const int chunk = swz ? (e / 8) ^ (r & 7) : e / 8;  // undo the 128B swizzle
     out[idx] = reinterpret_cast<uint16_t*>(smem + r * 128 + chunk * 16)[e % 8];
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int variant = argc > 1 ? atoi(argv[1]) : 0;  // 0: swizzle 128B, 1: no swizzle, 2: box of one patch row (ph box 1), 3: i box 16 (32-byte rows)
+
   const int N = 2, H = 224, W = 224, p = 16, Wp = W / p, Hp = H / p;
   std::vector<uint16_t> img(size_t(N) * 3 * H * W);
   for (size_t i = 0; i < img.size(); ++i) img[i] = uint16_t(i * 2654435761u >> 16);
@@ -59,17 +62,17 @@ int main() {
   CUtensorMap tm;
   cuuint64_t dims[5] = {cuuint64_t(p), cuuint64_t(p), cuuint64_t(Wp), cuuint64_t(Hp), cuuint64_t(N * 3)};
   cuuint64_t st[4] = {cuuint64_t(W) * 2, cuuint64_t(p) * 2, cuuint64_t(p) * W * 2, cuuint64_t(H) * W * 2};
-  const int ph_box = 7;
+  const int ph_box = variant == 2 ? 1 : 7;
   cuuint32_t box[5] = {cuuint32_t(p), 4, cuuint32_t(Wp), cuuint32_t(ph_box), 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dimg, dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  variant == 1 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   printf("encode (j, i, pw, ph, nc) with strides {2W, 2p, 2pW, 2HW}: CUresult %d\n", int(r));
   if (r != CUDA_SUCCESS) return 1;
   const int rows = Wp * ph_box, bytes = rows * 128;
   const int i0 = 8, ph0 = 7, nc = 4;  // channel 1 of image 1, patch rows 7..13, pixel rows 8..11 of each patch
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
-  probe<<<1, 128, 32768>>>(tm, dout, i0, ph0, nc, rows, bytes);
+  probe<<<1, 128, 32768>>>(tm, dout, i0, ph0, nc, rows, bytes, variant == 1 ? 0 : 1);
   cudaError_t e = cudaDeviceSynchronize();
   printf("kernel: %s\n", cudaGetErrorString(e));
   if (e != cudaSuccess) return 1;

@@ -187,12 +187,14 @@ def linear_fp8(x8: Tensor, w8: Tensor, acc_scale: Tensor, bias: Tensor | None, o
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale: float, causal: bool = False,
-              bias: Tensor | None = None) -> Tensor:
+              bias: Tensor | None = None, streaming: bool = False) -> Tensor:
     """q: (B, Lq, H*64) view, k/v: (B, Lkv, H*64) views sharing strides, out: (B, Lq, H*64).
 
     ``causal``: query i sees keys 0..i (top-left aligned like ``F.scaled_dot_product_attention(is_causal=True)``).
     ``bias``: fp32 (B, H, Lq, Lkv) view added to the scaled scores (``attn_mask`` of SDPA); broadcast dimensions may
-    have stride 0 (``Tensor.expand``), the last stride must be 1."""
+    have stride 0 (``Tensor.expand``), the last stride must be 1.
+    Unmasked calls with Lkv <= 256 run the single-pass kernel (csrc/attention_short.cuh); ``streaming=True`` forces the
+    online-softmax kernel there too (A/B measurements and tests)."""
     dev = _need_cuda(q, k, v, out, bias)
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, name)
@@ -219,7 +221,7 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Tensor, n_heads: int, scale:
         "b200enc_attention", dict(B=B, H=n_heads, Lq=Lq, Lkv=Lkv, causal=bool(causal)), dev,
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1), out.data_ptr(),
         out.stride(0), out.stride(1), B, n_heads, Lq, Lkv, D // n_heads, float(scale),
-        _lib.ATTN_CAUSAL if causal else 0,
+        (_lib.ATTN_CAUSAL if causal else 0) | (_lib.ATTN_GENERAL if streaming else 0),
     )
     return out
 

@@ -95,7 +95,7 @@ for rep, title in (("r2_c2_head", "C2 (ViT-B/16, batch 1024): patch rows, patch-
                 names = [short(d[idx["Kernel Name"]]) for d in data]
                 gemm = [t for n, t in zip(names, tot) if n.startswith("gemm_bf16")]
                 att = [t for n, t in zip(names, tot) if n.startswith("attention")]
-                layer = gemm[1:5] if len(gemm) >= 5 else gemm  # QKV, out_proj, FC1, FC2 of layer 0
+                layer = gemm[1:5]  # gemm[0] is the patch embedding; then QKV, out_proj, FC1, FC2 of layer 0 (in launch order)
                 traffic["c2_b1024"] = {
                     "gemm_mean_bytes_per_launch": sum(layer) / max(len(layer), 1),
                     "gemm_bytes_per_launch": dict(zip(["qkv", "out_proj", "fc1", "fc2"], layer)),

@@ -65,6 +65,49 @@ def test_attention_matches_sdpa(L):
     _close(out, want, 0.02, 0.02)
 
 
+@pytest.mark.parametrize("Lq,Lkv", [(1, 1), (16, 16), (33, 33), (64, 200), (128, 128), (130, 130), (192, 192), (193, 193),
+                                    (197, 197), (208, 208), (224, 224), (225, 225), (250, 250), (256, 256), (600, 250),
+                                    (700, 100), (1, 197)])
+def test_short_sequence_attention(Lq, Lkv):
+    """Lkv <= 256 without a mask takes the single-pass kernel (attention_short.cuh): every TMEM layout (rows up to 192,
+    224 and 256 keys), ragged row ends, one and many query-tile pairs, cross attention — against fp32 SDPA and against
+    the streaming kernel on the same inputs (two independent implementations of the same bf16 contract)."""
+    from pytorch_models_b200 import ops
+
+    B, H = 3, 5
+    g = torch.Generator(device="cuda").manual_seed(7 * Lq + Lkv)
+    q = (torch.randn(B, Lq, H * 64, device="cuda", generator=g) * 1.5).bfloat16()
+    kv = (torch.randn(B, Lkv, 2 * H * 64, device="cuda", generator=g) * 1.5).bfloat16()
+    k, v = kv[:, :, : H * 64], kv[:, :, H * 64:]
+    out = torch.full((B, Lq, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty_like(out)
+    ops.attention(q, k, v, out, H, 0.125)
+    ops.attention(q, k, v, ref, H, 0.125, streaming=True)
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(k), heads(v)).transpose(1, 2).flatten(-2)
+    _close(out, want, 0.02, 0.02)
+    _close(out, ref.float(), 0.02, 0.02)
+
+
+def test_short_sequence_attention_many_items():
+    """More work items than SMs x 2 stages: the operand ring, the TMEM hand-over between items and the staging buffers
+    of the output stores all wrap around many times (ViT-B/16 shape, 197 tokens, 12 heads)."""
+    from pytorch_models_b200 import ops
+
+    B, H, L = 96, 12, 197
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(B, L, 3 * H * 64, device="cuda", generator=g) * 2.0).bfloat16()
+    q, k, v = qkv[:, :, : H * 64], qkv[:, :, H * 64: 2 * H * 64], qkv[:, :, 2 * H * 64:]
+    out = torch.full((B, L, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, H, 0.125)
+    heads = lambda t: t.float().unflatten(-1, (H, 64)).transpose(1, 2)  # noqa: E731
+    want = F.scaled_dot_product_attention(heads(q), heads(k), heads(v)).transpose(1, 2).flatten(-2)
+    _close(out, want, 0.02, 0.02)
+    again = torch.empty_like(out)
+    ops.attention(q, k, v, again, H, 0.125)
+    assert torch.equal(out, again)  # deterministic
+
+
 @pytest.mark.parametrize("L", [1, 7, 128, 129, 200, 256, 257, 448, 700, 1024])
 def test_causal_attention_matches_sdpa(L):
     """is_causal=True of F.scaled_dot_product_attention (transformer.py:52,97): masked diagonal blocks, K/V blocks
