@@ -100,6 +100,19 @@ typedef struct b200enc_linear_args {
 
 int b200enc_linear(const b200enc_linear_args* args, void* stream);
 
+/*
+ * tokens[b][patch][:] = conv(img[b])[:, ph, pw] + bias + residual[patch][:]   (patch = ph * (W/16) + pw)
+ *
+ * nn.Conv2d(3, d, 16, 16) + flatten + transpose + positional embedding (image/vit.py:64,78-79) as ONE GEMM whose A
+ * operand is the NCHW bf16 image itself: no im2col / patch-row buffer (b200enc_patch_rows + b200enc_linear remain
+ * for other patch sizes and fp32 images). Uses the fields of b200enc_linear_args as follows: x = image
+ * [batches][3][img_h][img_w] bf16 contiguous (ldx, x_batch_stride ignored), w = conv.weight viewed as [N][768],
+ * M = (img_h/16)*(img_w/16), K = 768, bias, residual (required: the positional rows, res_batch_stride 0 broadcasts
+ * them), out / out_batch_stride / ldo (point `out` at token 1 of image 0 to leave room for a class token),
+ * stats_out / stats_rows_per_batch / stats_row_offset as in b200enc_linear; colsum, rowstats, flags must be 0.
+ */
+int b200enc_patch_embed16(const b200enc_linear_args* args, int img_h, int img_w, void* stream);
+
 /* flags for b200enc_attention */
 #define B200ENC_ATTN_CAUSAL 1 /* key j only visible to queries i >= j (is_causal=True of SDPA: DecoderLayer, transformer.py:97) */
 #define B200ENC_ATTN_GENERAL 131072 /* debug / A-B: use the streaming (online-softmax) kernel even where the short-sequence kernel applies */

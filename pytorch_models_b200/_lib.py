@@ -67,6 +67,7 @@ _SIGNATURES = {
     "b200enc_row_stats": (c_int, [c_void_p, c_longlong, c_float, c_int, c_int, c_void_p, c_void_p]),
     "b200enc_mean_tokens": (
         c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p]),
+    "b200enc_patch_embed16": (c_int, [ctypes.POINTER(LinearArgs), c_int, c_int, c_void_p]),
     "b200enc_patch_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200enc_cls_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "b200enc_embed_rows": (

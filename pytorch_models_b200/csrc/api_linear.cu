@@ -7,10 +7,10 @@ using namespace b200;
 
 namespace {
 
-template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats, bool kF8 = false>
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTma, bool kStats, bool kF8 = false, bool kPatch = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats, kF8>;
+  auto kern = gemm_bf16_kernel<kCtas, kFold, kAct, kRes, kTma, kStats, kF8, kPatch>;
   constexpr int kSmem = GemmSmem<kCtas, kRes>::kBytes;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), kSmem)) return rc;
   cudaLaunchConfig_t cfg = {};
@@ -75,6 +75,68 @@ int dispatch_epilogue(int sel, bool tma, bool stats, const CUtensorMap& ta, cons
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------- im2col-free patch embedding (p = 16)
+extern "C" int b200enc_patch_embed16(const b200enc_linear_args* a, int img_h, int img_w, void* stream) {
+  if (int rc0 = check_abort("b200enc_patch_embed16")) return rc0;
+  B200_CHECK_ARG(a != nullptr && a->x && a->w && a->out && a->residual, "b200enc_patch_embed16: null image / weight / output / residual");
+  B200_CHECK_ARG(img_h >= 16 && img_w >= 16 && img_h % 16 == 0 && img_w % 16 == 0,
+                 "b200enc_patch_embed16: image %d x %d is not a multiple of the 16-pixel patch", img_h, img_w);
+  const int hp = img_h / 16, wp = img_w / 16, P = hp * wp, n = a->batches, N = a->N;
+  B200_CHECK_ARG(n >= 1 && a->M == P && a->K == 768 && N >= 8 && N % 8 == 0,
+                 "b200enc_patch_embed16: expects M = %d patches, K = 768, got M=%d K=%d N=%d", P, a->M, a->K, N);
+  B200_CHECK_ARG(a->colsum == nullptr && a->flags == 0 && a->ldw >= 768 && a->ldo >= N && a->ldr >= N,
+                 "b200enc_patch_embed16: bias + positional rows (+ statistics) only");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && a->ldo % 8 == 0 && a->out_batch_stride % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 && a->ldr % 8 == 0,
+                 "b200enc_patch_embed16: output and residual rows must be 16-byte aligned");
+  B200_CHECK_ARG((long long)n * 3 * hp < (1ll << 31), "b200enc_patch_embed16: too many image planes");
+  CUtensorMap ta, tb;
+  int rc;
+  // see the kPatch comment in gemm.cuh (5-D no-swizzle form kept for A/B: -DGEMM_PATCH_SW32=0)
+  const uint64_t dims[5] = {8, uint64_t(n) * 3 * hp, 2, 16, uint64_t(wp)};
+  const uint64_t strides[4] = {uint64_t(16) * img_w * 2, 16, uint64_t(img_w) * 2, 32};
+  const uint32_t box[5] = {8, 8, 2, 4, 16};
+#if GEMM_PATCH_SW32
+  const uint64_t dims4[4] = {16, uint64_t(n) * 3 * hp, 16, uint64_t(wp)};
+  const uint64_t strides4[3] = {uint64_t(16) * img_w * 2, uint64_t(img_w) * 2, 32};
+  const uint32_t box4[4] = {16, 8, 4, 16};
+  (void)dims, (void)strides, (void)box;
+  if ((rc = make_tmap_bf16_nd(&ta, a->x, 4, dims4, strides4, box4, 32))) return rc;
+#else
+  if ((rc = make_tmap_bf16_nd(&ta, a->x, 5, dims, strides, box, 0))) return rc;
+#endif
+  if ((rc = make_tmap_bf16(&tb, a->w, 768, N, 0, a->ldw, 0, GEMM_BK, GEMM_BN, 128))) return rc;
+  GemmParams p = {};
+  p.M = P;
+  p.N = N;
+  p.K = 768;
+  p.batches = n;
+  p.pt_hp = hp;
+  p.pt_wp = wp;
+  p.pt_nw16 = (wp + 15) / 16;
+  p.tiles_m = ((hp + 7) / 8) * p.pt_nw16;
+  p.tiles_n = (N + GEMM_BN - 1) / GEMM_BN;
+  p.bias = a->bias;
+  p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  p.stats_rows = a->stats_rows_per_batch > 0 ? a->stats_rows_per_batch : P;
+  p.stats_off = a->stats_row_offset;
+  B200_CHECK_ARG(a->stats_row_offset >= 0 && p.stats_rows >= P + a->stats_row_offset,
+                 "b200enc_patch_embed16: stats_rows_per_batch=%d cannot hold %d rows at offset %d", p.stats_rows, P,
+                 a->stats_row_offset);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.res_batch_stride = a->res_batch_stride;
+  p.ldr = a->ldr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.out_batch_stride = a->out_batch_stride;
+  p.ldo = a->ldo;
+  p.abort_word = abort_word();
+  const long long total = (long long)p.tiles_m * p.tiles_n * n;
+  const int grid = int(total < sm_count() ? total : sm_count());
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->stats_out != nullptr) return launch_gemm<1, false, 0, true, false, true, false, true>(ta, tb, tb, p, grid, s);
+  return launch_gemm<1, false, 0, true, false, false, false, true>(ta, tb, tb, p, grid, s);
+}
 
 extern "C" int b200enc_linear(const b200enc_linear_args* a, void* stream) {
   B200_CHECK_ARG(a != nullptr, "b200enc_linear: null argument struct");

@@ -19,6 +19,11 @@
 
 namespace b200 {
 
+// kPatch A operand: 1 = 4-D tensor map + 32-byte swizzle (32-byte TMA rows: 0.368 ms for the C2 patch embedding),
+// 0 = 5-D map + no swizzle (16-byte rows: 0.457 ms); both parity-green (b200enc_selftest patch:all)
+#ifndef GEMM_PATCH_SW32
+#define GEMM_PATCH_SW32 1
+#endif
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
@@ -73,6 +78,9 @@ struct GemmParams {
   long long out_batch_stride;
   int ldo;
   const float* acc_scale;  // kF8 only: device scalar, dequantisation scale of the accumulator
+  // kPatch only (im2col-free patch embedding, p = 16): patch grid of one image and the tiling of its rows. An M tile is
+  // 8 patch rows x 16 patch columns: tile row r <-> patch (ph0 + r % 8, pw0 + r / 8), tiles_m = pt_nph8 * pt_nw16.
+  int pt_hp, pt_wp, pt_nw16;
   int debug;  // timing experiments only: bit0 = skip the output store, bit1 = skip the whole epilogue body
   unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
 };
@@ -116,7 +124,15 @@ __device__ __forceinline__ float2 silu_fast2(float2 x) {
 // kF8: operands are e4m3 bytes (the optional FP8 variant, b200enc.h B200ENC_LINEAR_FP8): a stage still holds 128-byte
 // rows, i.e. 128 instead of 64 K elements, each tcgen05.mma (kind::f8f6f4) consumes K = 32, and the accumulator is
 // multiplied by *p.acc_scale (the product of the two per-tensor dequantisation scales) before the bias is added.
-template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats, bool kF8 = false>
+// kPatch: the A operand is the NCHW bf16 image itself (nn.Conv2d(3, d, 16, 16) as a GEMM without an im2col buffer,
+// image/vit.py:64,78). tmA is a 4-D view (16 pixels, plane*Hp + ph, pixel row, pw) with byte strides (2, 16W*2, 2W, 32)
+// and the 32-byte swizzle: ONE box (16, 8, 4, 16) per K block (one channel, four pixel rows: K index c*256 + i*16 + j,
+// the order of conv.weight.view(d, 768)) lands in shared memory as [pw][i][ph % 8][16 pixels] — for every (pw, i) an
+// 8-row x 32-byte atom of a K-major SWIZZLE_32B operand, one MMA K step wide (256 B between K steps, 1024 B between
+// 8-row groups). The 128-byte swizzle of the other GEMMs cannot be produced from NCHW: a 32-byte inner box is padded to
+// 128-byte rows there (csrc/probe_im2col_tma.cu). Rows of a tile are patches in (pw, ph % 8) order, so the epilogue maps
+// tile row -> token row and stores per thread (kTmaStore = false); patches outside the grid are zero-filled / skipped.
+template <int kCtas, bool kFold, int kAct, bool kRes, bool kTmaStore, bool kStats, bool kF8 = false, bool kPatch = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -202,6 +218,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
             tma_load_3d_2cta(&tmA, leader_full, sa, kb * kBKe, m0, b);
             tma_load_2d_2cta(&tmB, leader_full, sa + GEMM_A_BYTES, kb * kBKe, n0);
+          } else if (kPatch) {
+            const int tm = r / p.tiles_n;
+            mbar_expect_tx(full_bar(stage), kStageBytes);
+#if GEMM_PATCH_SW32
+            tma_load_4d(&tmA, full_bar(stage), sa, 0, (b * 3 + (kb >> 2)) * p.pt_hp + 8 * (tm / p.pt_nw16), (kb & 3) * 4,
+                        16 * (tm % p.pt_nw16));
+#else
+            tma_load_5d(&tmA, full_bar(stage), sa, 0, (b * 3 + (kb >> 2)) * p.pt_hp + 8 * (tm / p.pt_nw16), 0, (kb & 3) * 4,
+                        16 * (tm % p.pt_nw16));
+#endif
+            tma_load_2d(&tmB, full_bar(stage), sa + GEMM_A_BYTES, kb * kBKe, n0);
           } else {
             mbar_expect_tx(full_bar(stage), kStageBytes);
             tma_load_3d(&tmA, full_bar(stage), sa, kb * kBKe, m0, b);
@@ -228,7 +255,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(full_bar(stage), phase, wctx);
           tc_fence_after();
           const uint32_t sa = ring + stage * kStageBytes;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+#if GEMM_PATCH_SW32
+          const uint64_t da = kPatch ? make_smem_desc_sw32(sa, 256, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+#else
+          const uint64_t da = kPatch ? make_smem_desc_nosw(sa, 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+#endif
+          constexpr uint32_t kAStep = kPatch ? 16u : 2u;  // 16 K elements further: two 128-byte core matrices / 32 bytes in the swizzle atom
           const uint64_t db = make_smem_desc_sw128(sa + GEMM_A_BYTES, 16, 1024);
           if (elect_one()) {
 #pragma unroll
@@ -236,13 +268,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               // advancing K by 16 bf16 (32 e4m3) = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
               if (kF8) {
                 if (kCtas == 2)
-                  umma_ss_f8_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  umma_ss_f8_2cta(d_tmem, da + kAStep * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
                 else
-                  umma_ss_f8(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  umma_ss_f8(d_tmem, da + kAStep * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
               } else if (kCtas == 2)
-                umma_ss_2cta(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_ss_2cta(d_tmem, da + kAStep * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
               else
-                umma_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_ss(d_tmem, da + kAStep * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if (kCtas == 2) umma_commit_2cta(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
             if (kb == num_kb - 1) {
@@ -275,8 +307,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int r = tile - b * tiles_per_batch;
       const int m0 = (r / p.tiles_n) * kTileM + int(cta_rank) * GEMM_BM;  // first row owned by this CTA
       const int n0 = (r % p.tiles_n) * GEMM_BN;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      // row of the batch this lane owns. kPatch: tile row -> patch index (see the kernel comment)
+      const int pt_ph0 = kPatch ? 8 * ((r / p.tiles_n) / p.pt_nw16) : 0;
+      const int pt_pw0 = kPatch ? 16 * ((r / p.tiles_n) % p.pt_nw16) : 0;
+      auto tile_row = [&](int rt, bool& ok) {  // rt = row inside this CTA's 128-row tile
+        if (kPatch) {
+          const int ph = pt_ph0 + (rt & 7), pw = pt_pw0 + (rt >> 3);
+          ok = ph < p.pt_hp && pw < p.pt_wp;
+          return ph * p.pt_wp + pw;
+        }
+        ok = m0 + rt < p.M;
+        return m0 + rt;
+      };
+      bool row_ok;
+      const int row = tile_row(q * 32 + lane, row_ok);
       const int nh = n0 + hf * 128;  // first column owned by this warp
 
       // ---- issue every global load of this tile up front: they complete while the tile's main loop still runs
@@ -310,10 +354,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int rr = m0 + q * 32 + 4 * j + (lane >> 3);
+            bool rr_ok;
+            const int rr = tile_row(q * 32 + 4 * j + (lane >> 3), rr_ok);
             const int col = cc * 64 + (lane & 7) * 8;
             rres[cc][j] = make_uint4(0, 0, 0, 0);
-            if (rr < p.M && nh + col < p.N)
+            if (rr_ok && nh + col < p.N)
               rres[cc][j] = __ldg(reinterpret_cast<const uint4*>(res_base + (long long)rr * p.ldr + col));
           }
       }

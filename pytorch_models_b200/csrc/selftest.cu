@@ -662,6 +662,123 @@ static bool run_patch(int B, int HW, int p, bool f32) {
   return report("patch_rows", st);
 }
 
+// im2col-free patch embedding (b200enc_patch_embed16): tokens[b][off + patch] = conv(img)[patch] + bias + pe[patch],
+// optional LayerNorm partial statistics of the stored rows; fp64 CPU check of every output, guard bands around the
+// token buffer (the class-token rows and the tail must stay untouched).
+static bool run_patch_embed(int n, int H, int W, int N, int tok_off, bool stats, int iters) {
+  const int hp = H / 16, wp = W / 16, P = hp * wp, L = P + tok_off, K = 768;
+  printf("patch_embed16 n=%d %dx%d N=%d token offset %d stats=%d\n", n, H, W, N, tok_off, int(stats));
+  fflush(stdout);
+  std::vector<uint16_t> himg = rand_bf16(size_t(n) * 3 * H * W, 1.0f, false);
+  std::vector<uint16_t> hw = rand_bf16(size_t(N) * K, 0.06f, false);
+  std::vector<uint16_t> hpe = rand_bf16(size_t(P) * N, 1.0f, false);
+  std::vector<float> hbias(N);
+  for (auto& v : hbias) v = urand();
+  const int n_sl = (N + 127) / 128;
+  DevBuf dimg(himg.size() * 2), dw(hw.size() * 2), dpe(hpe.size() * 2), dbias(N * 4);
+  GuardedBuf gtok(size_t(n) * L * N * 2), gst(size_t(n) * L * n_sl * 8);
+  CK(cudaMemcpy(dimg.p, himg.data(), himg.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dpe.p, hpe.data(), hpe.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias.p, hbias.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(gtok.p(), 0x7f, gtok.bytes));
+  CK(cudaMemset(gst.p(), 0x7f, gst.bytes));
+  b200enc_linear_args a;
+  memset(&a, 0, sizeof(a));
+  a.x = dimg.p;
+  a.w = dw.p;
+  a.ldw = K;
+  a.bias = (const float*)dbias.p;
+  a.residual = dpe.p;
+  a.res_batch_stride = 0;
+  a.ldr = N;
+  a.out = (uint16_t*)gtok.p() + size_t(tok_off) * N;
+  a.out_batch_stride = (long long)L * N;
+  a.ldo = N;
+  a.stats_out = stats ? (float*)gst.p() : nullptr;
+  a.stats_rows_per_batch = L;
+  a.stats_row_offset = tok_off;
+  a.batches = n;
+  a.M = P;
+  a.N = N;
+  a.K = K;
+  auto call = [&]() { return b200enc_patch_embed16(&a, H, W, nullptr); };
+  int rc = call();
+  if (rc) {
+    printf("  [FAIL] rc=%d: %s\n", rc, b200enc_last_error());
+    return false;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("  [FAIL] kernel error: %s\n", cudaGetErrorString(e));
+    return false;
+  }
+  std::vector<uint16_t> ho(size_t(n) * L * N);
+  std::vector<float> hs(size_t(n) * L * n_sl * 2);
+  CK(cudaMemcpy(ho.data(), gtok.p(), ho.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hs.data(), gst.p(), hs.size() * 4, cudaMemcpyDeviceToHost));
+  CmpStat st, sst;
+  long untouched_bad = 0;
+  std::vector<float> arow(K);
+  const int bstep = n > 4 ? n / 4 : 1;
+  for (int b = 0; b < n; b += bstep) {
+    for (int t = 0; t < tok_off; ++t)
+      for (int c = 0; c < N; ++c) untouched_bad += ho[(size_t(b) * L + t) * N + c] != 0x7f7f;
+    for (int pt = 0; pt < P; ++pt) {
+      const int ph = pt / wp, pw = pt % wp;
+      for (int k = 0; k < K; ++k) {
+        const int c = k / 256, i = (k / 16) % 16, j = k % 16;
+        arow[k] = bf2f(himg[((size_t(b) * 3 + c) * H + ph * 16 + i) * W + pw * 16 + j]);
+      }
+      std::vector<double> orow(N);
+      for (int c = 0; c < N; ++c) {
+        double acc = 0;
+        const uint16_t* wr = &hw[size_t(c) * K];
+        for (int k = 0; k < K; ++k) acc += double(arow[k]) * double(bf2f(wr[k]));
+        acc += hbias[c] + bf2f(hpe[size_t(pt) * N + c]);
+        const float got = bf2f(ho[(size_t(b) * L + tok_off + pt) * N + c]);
+        cmp_one(st, acc, got, 0.02, 0.01, b * P + pt, c, "patch_embed16");
+        orow[c] = got;  // statistics are those of the stored values
+      }
+      if (stats)
+        for (int sl = 0; sl < n_sl; ++sl) {
+          const int c0 = sl * 128, c1 = std::min(N, c0 + 128);
+          double mean = 0, m2 = 0;
+          for (int c = c0; c < c1; ++c) mean += orow[c];
+          mean /= (c1 - c0);
+          for (int c = c0; c < c1; ++c) m2 += (orow[c] - mean) * (orow[c] - mean);
+          const float* g = &hs[((size_t(b) * L + tok_off + pt) * n_sl + sl) * 2];
+          cmp_one(sst, mean, g[0], 1e-3, 1e-3, b * P + pt, sl, "patch_embed16 mean");
+          cmp_one(sst, m2, g[1], 1e-2, 1e-3, b * P + pt, sl, "patch_embed16 M2");
+        }
+    }
+  }
+  bool ok = report("patch_embed16", st);
+  if (stats) ok = report("patch_embed16 statistics", sst) && ok;
+  if (untouched_bad) {
+    printf("  [FAIL] %ld class-token elements were overwritten\n", untouched_bad);
+    ok = false;
+  }
+  ok = gtok.intact("patch_embed16 tokens") && ok;
+  ok = gst.intact("patch_embed16 statistics") && ok;
+  if (ok && iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) call();
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) call();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    printf("  time patch_embed16: %.3f ms  %.1f TFLOP/s  %.1f GB/s (image in, tokens out, pe)\n", ms,
+           2.0 * n * P * N * K / ms * 1e-9, (2.0 * n * 3 * H * W + 2.0 * n * P * N) / ms * 1e-6);
+  }
+  return ok;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     printf("usage: %s <case>|list\n", argv[0]);
@@ -700,6 +817,19 @@ int main(int argc, char** argv) {
     run_attn_trace(argc > 2 ? atoi(argv[2]) : 128, argc > 3 ? atoi(argv[3]) : 12, argc > 4 ? atoi(argv[4]) : 197);
   }
 #endif
+  if (which == "patch:all" || which == "patch:perf") {
+    found = true;
+    if (which == "patch:all") {
+      ok = run_patch_embed(2, 224, 224, 768, 1, true, 0) && ok;
+      ok = run_patch_embed(1, 384, 384, 1024, 0, false, 0) && ok;   // 24 x 24 patches: 3 x 2 tiles per image
+      ok = run_patch_embed(3, 64, 48, 256, 1, true, 0) && ok;        // 4 x 3 patches: one sparse tile
+      ok = run_patch_embed(5, 16, 16, 64, 0, true, 0) && ok;         // a single patch per image
+      ok = run_patch_embed(2, 272, 400, 384, 1, true, 0) && ok;      // 17 x 25 patches: ragged in both directions
+      ok = run_patch_embed(300, 32, 32, 128, 1, false, 0) && ok;     // more tiles than SMs
+    } else {
+      ok = run_patch_embed(1024, 224, 224, 768, 1, true, 10) && ok;
+    }
+  }
   if (which == "rows:all") {
     found = true;
     ok = run_layernorm(1000, 768, 1e-6f, 1, 0) && ok;

@@ -143,14 +143,19 @@ class ViT(nn.Module):
             raise ValueError(f"image {H}x{W} gives {P} patches but pe has {self.pe.shape[1]}; call resize_pe first")
         d = self.patch_embed.out_channels
         off = 0 if self.cls_token is None else 1
-        rows = torch.empty(N, P, pk.kpad, device=imgs.device, dtype=torch.bfloat16)
         tokens = torch.empty(N, P + off, d, device=imgs.device, dtype=torch.bfloat16)
-        ops.patch_rows(imgs, p, pk.kpad, rows)
         stats = None
         if with_stats and self.layers.wants_stats():
             stats = torch.empty(N, P + off, (d + 127) // 128, 2, device=imgs.device, dtype=torch.float32)
-        ops.linear(rows, pk.w, pk.bias, tokens[:, off:, :], residual=pk.pe, stats_out=stats, stats_rows=P + off,
-                   stats_row_offset=off)
+        if p == 16 and imgs.dtype == torch.bfloat16 and tuple(self.patch_embed.kernel_size) == (16, 16) and N * 3 * (H // 16) < 2 ** 31:
+            # im2col-free: the GEMM's A operand is the NCHW image itself (5-D tensor map, csrc/gemm.cuh kPatch)
+            ops.patch_embed16(imgs, pk.w, pk.bias, pk.pe.view(P, d), tokens[:, off:, :], stats_out=stats,
+                              stats_rows=P + off, stats_row_offset=off)
+        else:  # other patch sizes (DINOv2: 14) and fp32 images: materialised patch rows (the kernel converts fp32 -> bf16)
+            rows = torch.empty(N, P, pk.kpad, device=imgs.device, dtype=torch.bfloat16)
+            ops.patch_rows(imgs, p, pk.kpad, rows)
+            ops.linear(rows, pk.w, pk.bias, tokens[:, off:, :], residual=pk.pe, stats_out=stats, stats_rows=P + off,
+                       stats_row_offset=off)
         if off:
             ops.cls_rows(pk.cls, tokens)
             if stats is not None:

@@ -268,6 +268,41 @@ def mean_tokens(x: Tensor, out: Tensor) -> Tensor:
     return out
 
 
+def patch_embed16(imgs: Tensor, w: Tensor, bias: Tensor, pe: Tensor, tokens: Tensor, *, stats_out: Tensor | None = None,
+                  stats_rows: int = 0, stats_row_offset: int = 0) -> Tensor:
+    """tokens[b, patch, :] = conv16x16(imgs[b])[patch] + bias + pe[patch]: the patch embedding of a 16-pixel-patch ViT
+    (``nn.Conv2d(3, d, 16, 16)`` + flatten/transpose + ``pe``, image/vit.py:64,78-79) as ONE GEMM that reads the NCHW
+    bf16 image through a 5-D tensor map — no im2col buffer (other patch sizes / fp32 images: `patch_rows` + `linear`).
+
+    imgs: (N, 3, H, W) bf16 contiguous, H and W multiples of 16; w: (d, 768) bf16 = ``conv.weight.view(d, -1)``;
+    bias: (d,) fp32; pe: (P, d) bf16 with P = (H/16)*(W/16); tokens: (N, P, d) bf16 view (row stride >= d, e.g.
+    ``buf[:, 1:, :]`` behind a class token). ``stats_out`` as in `linear`."""
+    dev = _need_cuda(imgs, w, bias, pe, tokens, stats_out)
+    _need(imgs, torch.bfloat16, "imgs"), _need(w, torch.bfloat16, "w"), _need(pe, torch.bfloat16, "pe")
+    _need(tokens, torch.bfloat16, "tokens"), _need(bias, torch.float32, "bias"), _need(stats_out, torch.float32, "stats_out")
+    if imgs.dim() != 4 or imgs.shape[1] != 3 or not imgs.is_contiguous():
+        raise ValueError("images must be a contiguous (N, 3, H, W) tensor")
+    N, _, H, W = imgs.shape
+    if H % 16 or W % 16:
+        raise ValueError(f"image {H}x{W} is not a multiple of the 16-pixel patch")
+    P, d = (H // 16) * (W // 16), w.shape[0]
+    if w.shape != (d, 768) or w.stride(1) != 1 or bias.shape != (d,) or pe.shape != (P, d) or pe.stride(1) != 1:
+        raise ValueError(f"shape mismatch: w {tuple(w.shape)}, bias {tuple(bias.shape)}, pe {tuple(pe.shape)} for {P} patches")
+    if tokens.shape != (N, P, d) or tokens.stride(2) != 1:
+        raise ValueError(f"tokens must be a ({N}, {P}, {d}) view with unit inner stride, got {tuple(tokens.shape)}")
+    srows = stats_rows if stats_rows > 0 else P
+    if stats_out is not None and (not stats_out.is_contiguous() or srows < P + stats_row_offset or stats_row_offset < 0
+                                  or stats_out.numel() != 2 * N * srows * ((d + 127) // 128)):
+        raise ValueError("stats_out must be a contiguous (N*rows, ceil(d/128), 2) tensor that holds every row")
+    args = _lib.LinearArgs(
+        imgs.data_ptr(), 0, 0, w.data_ptr(), w.stride(0), _ptr(bias), None, None, 0, 0.0, pe.data_ptr(), 0, pe.stride(0),
+        tokens.data_ptr(), tokens.stride(0), tokens.stride(1), _ptr(stats_out), N, P, d, 768, 0, int(stats_rows),
+        int(stats_row_offset), None,
+    )
+    _call("b200enc_patch_embed16", dict(B=N, H=H, W=W, N=d), dev, ctypes.byref(args), H, W)
+    return tokens
+
+
 def patch_rows(imgs: Tensor, patch: int, kpad: int, rows: Tensor) -> Tensor:
     dev = _need_cuda(imgs, rows)
     if imgs.dtype == torch.bfloat16:

@@ -362,3 +362,60 @@ def test_fused_layernorm_statistics_chain(M, d, N):
         ops.linear(x, pk.w, pk.bias, out2, colsum=pk.colsum, rowstats=stats)
     _close(out, want, 0.03, 0.02)
     _close(out, out2, 0.01, 0.01)
+
+
+@pytest.mark.parametrize("n,H,W,d,cls", [(2, 224, 224, 768, True), (1, 384, 384, 1024, False), (3, 64, 48, 256, True),
+                                         (5, 16, 16, 64, False), (2, 272, 400, 384, True), (200, 32, 32, 128, True)])
+def test_patch_embed16_matches_conv2d(n, H, W, d, cls):
+    """The im2col-free patch embedding (b200enc_patch_embed16: the GEMM reads the NCHW image through a 5-D tensor map)
+    against ``F.conv2d(stride=16)`` + flatten/transpose + pe in fp32 (image/vit.py:64,78-79), with and without room for
+    a class token, ragged patch grids, more tiles than SMs; its fused LayerNorm statistics against the stored rows; and
+    against the materialised-patch-row path (patch_rows + linear) on the same inputs."""
+    from pytorch_models_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + H + W)
+    imgs = torch.randn(n, 3, H, W, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(d, 3, 16, 16, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(d, device="cuda", generator=g)
+    P = (H // 16) * (W // 16)
+    pe = torch.randn(P, d, device="cuda", generator=g).bfloat16()
+    off = 1 if cls else 0
+    tokens = torch.full((n, P + off, d), 7.0, device="cuda", dtype=torch.bfloat16)
+    n_sl = (d + 127) // 128
+    stats = torch.full((n, P + off, n_sl, 2), -3.0, device="cuda")
+    ops.patch_embed16(imgs, w.view(d, 768), bias, pe, tokens[:, off:, :], stats_out=stats, stats_rows=P + off,
+                      stats_row_offset=off)
+    want = F.conv2d(imgs.float(), w.float(), bias, stride=16).flatten(2).transpose(1, 2) + pe.float()
+    _close(tokens[:, off:], want, 0.03, 0.01)
+    if cls:  # the class-token rows (and their statistics) are not touched
+        assert torch.all(tokens[:, 0] == 7.0) and torch.all(stats[:, 0] == -3.0)
+    got = tokens[:, off:].float()
+    pad = n_sl * 128 - d
+    sl = F.pad(got, (0, pad)).unflatten(-1, (n_sl, 128))
+    cnt = torch.tensor([min(128, d - 128 * i) for i in range(n_sl)], device="cuda", dtype=torch.float32)
+    mean = sl.sum(-1) / cnt
+    mask = (torch.arange(128, device="cuda")[None, :] < cnt[:, None]).float()
+    m2 = (((sl - mean[..., None]) ** 2) * mask).sum(-1)
+    assert torch.allclose(stats[:, off:, :, 0], mean, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(stats[:, off:, :, 1], m2, atol=2e-2, rtol=2e-3)
+    # the other path: materialised patch rows + the generic GEMM
+    rows = torch.empty(n, P, 768, device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty(n, P, d, device="cuda", dtype=torch.bfloat16)
+    ops.patch_rows(imgs, 16, 768, rows)
+    ops.linear(rows, w.view(d, 768), bias, ref, residual=pe.unsqueeze(0))
+    _close(tokens[:, off:], ref.float(), 0.02, 0.01)
+
+
+def test_patch_embed16_rejects_bad_arguments():
+    from pytorch_models_b200 import ops
+
+    imgs = torch.zeros(1, 3, 40, 32, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(64, 768, device="cuda", dtype=torch.bfloat16)
+    bias = torch.zeros(64, device="cuda")
+    with pytest.raises(ValueError):
+        ops.patch_embed16(imgs, w, bias, torch.zeros(4, 64, device="cuda", dtype=torch.bfloat16),
+                          torch.zeros(1, 4, 64, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(TypeError):
+        ops.patch_embed16(torch.zeros(1, 3, 32, 32, device="cuda"), w, bias,
+                          torch.zeros(4, 64, device="cuda", dtype=torch.bfloat16),
+                          torch.zeros(1, 4, 64, device="cuda", dtype=torch.bfloat16))
