@@ -17,15 +17,33 @@ extern "C" void b200enc_debug_attention_trace(long long* buf) { g_attention_trac
 #endif
 
 namespace {
+// one launch path for every attention kernel: programmatic dependent launch unless disabled (host_util.h)
+template <typename Kern, typename Params>
+int launch_pdl(Kern kern, int grid, int threads, int smem, cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tk,
+               const CUtensorMap& tv, const CUtensorMap& to, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, to, p));
+  return 0;
+}
+
 int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                      const AttnParams& p, cudaStream_t s) {
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (p.bias != nullptr) {
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<true>), ATT_SMEM_BYTES)) return rc;
-    attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
+    return launch_pdl(attention_kernel<true>, grid, ATT_THREADS, ATT_SMEM_BYTES, s, tq, tk, tv, to, p);
   } else {
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<false>), ATT_SMEM_BYTES)) return rc;
-    attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tk, tv, to, p);
+    return launch_pdl(attention_kernel<false>, grid, ATT_THREADS, ATT_SMEM_BYTES, s, tq, tk, tv, to, p);
   }
   B200_CUDA(cudaGetLastError());
   return 0;
@@ -76,9 +94,7 @@ static int attention_short_impl(const void* q, long long q_batch_stride, int ldq
   // the row length of ViT at 224 px (197 tokens -> 13 halves of 16 columns) has its own instantiation
   auto kern = p.nk16 == 208 ? attention_short_kernel<13> : attention_short_kernel<0>;
   if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), ATS_SMEM_BYTES))) return rc;
-  kern<<<grid, ATT_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, to, p);
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(kern, grid, ATT_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, to, p);
 }
 #endif
 

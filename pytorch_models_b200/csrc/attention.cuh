@@ -255,6 +255,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (ptx.cuh: programmatic dependent launch; nothing above touched global memory)
+  griddep_wait();
   // per tile t: S at t*256 + [0,128) (P aliases [0,64)), O accumulator at t*256 + [128,192)
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
   // K/V blocks a query tile has to visit: all of them, or with a causal mask only those up to its last row's diagonal

@@ -124,6 +124,8 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (ptx.cuh: programmatic dependent launch; nothing above touched global memory)
+  griddep_wait();
   const int n_my = p.n_items > int(blockIdx.x) ? (p.n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
   auto item_of = [&](int n) { return int(blockIdx.x) + n * int(gridDim.x); };
   auto two_of = [&](int item) { return (item % p.n_qp) * 256 + ATT_BQ < p.Lq; };  // second query tile has a valid row

@@ -191,6 +191,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared / tensor memory: it may overlap the previous kernel's tail
+  griddep_launch_dependents();
+  griddep_wait();
 
   constexpr int kBKe = kF8 ? 2 * GEMM_BK : GEMM_BK;  // K elements per 128-byte stage row
   const int num_kb = (p.K + kBKe - 1) / kBKe;

@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "host_util.h"
 
 #include <string.h>
@@ -162,6 +163,14 @@ int sm_count() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   counts[dev] = n;
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200ENC_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int ensure_dynamic_smem(const void* kernel, int bytes) {

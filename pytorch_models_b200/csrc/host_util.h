@@ -52,6 +52,9 @@ int sm_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch.
 int ensure_dynamic_smem(const void* kernel, int bytes);
 
+// Programmatic dependent launch for the tensor-core kernels (GEMM, attention): on unless B200ENC_PDL=0 in the environment.
+bool pdl_enabled();
+
 // The abort word: one unsigned int in mapped, portable host memory (readable by the host without synchronising,
 // writable by every device). 0 = healthy. Device-side waits that exceed their time limit store a non-zero code; every
 // entry point calls check_abort() first and refuses to enqueue more work once it is set.

@@ -103,6 +103,13 @@ __device__ __forceinline__ void mbar_wait_plain(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor on the stream is still draining; `griddep_wait` blocks until the predecessor
+// has completed and its memory is visible, and must come before the first global access. `griddep_launch_dependents`
+// lets the successor's CTAs be scheduled as soon as resources free up.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Wait that parks the warp in hardware: mbarrier.try_wait with an explicit suspend-time hint stays suspended until the
 // phase completes (or the hint runs out) instead of coming back after a few dozen clocks, so a waiting warp issues
 // almost nothing and leaves its sub-partition's issue slots to the warps that compute.
