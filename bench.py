@@ -413,6 +413,11 @@ def main() -> None:
     if not args.no_e2e:
         e2e = e2e_leg(torch.bfloat16)
         e2e_f32 = e2e_leg(torch.float32)  # what the reference's callers hold (tests/image/test_vit.py:11)
+        if os.environ.get("B200_BENCH_E2E_REPEAT"):  # experiment: does the order of the legs matter?
+            again = e2e_leg(torch.bfloat16)
+            if rank == 0:
+                print(f"[e2e repeat] bf16 first {e2e['ms_per_step']:.3f} ms, fp32 {e2e_f32['ms_per_step']:.3f} ms, "
+                      f"bf16 again {again['ms_per_step']:.3f} ms", file=sys.stderr, flush=True)
 
     # ---- N > 1: the optional NCCL all-gather of the embeddings, once, outside every timed region, checked bit for bit
     # against the same global batch run on one GPU (no cross-rank arithmetic exists, so it must be exact)
