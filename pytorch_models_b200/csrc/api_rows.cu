@@ -19,6 +19,32 @@ static int check_rows(const char* who, const void* x, long long ldx, int rows, i
   return 0;
 }
 
+// persistent grid: enough warps to fill every SM several times over, never more than one warp per row
+template <bool kWriteOut>
+static int launch_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, int rows, int d,
+                            void* out, long long ldo, float* stats, void* stream) {
+  const int blocks_needed = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int grid = std::min(blocks_needed, sm_count() * 8);
+  const int nc = (d / 8 + 31) / 32;
+  auto go = [&](auto kern) {
+    kern<<<grid, LN_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, rows, d, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+        reinterpret_cast<float2*>(stats));
+  };
+  switch (nc) {
+    case 1: go(layernorm_kernel<kWriteOut, 1>); break;
+    case 2: go(layernorm_kernel<kWriteOut, 2>); break;
+    case 3: go(layernorm_kernel<kWriteOut, 3>); break;
+    case 4: go(layernorm_kernel<kWriteOut, 4>); break;
+    case 5: go(layernorm_kernel<kWriteOut, 5>); break;
+    case 6: go(layernorm_kernel<kWriteOut, 6>); break;
+    case 7: go(layernorm_kernel<kWriteOut, 7>); break;
+    default: go(layernorm_kernel<kWriteOut, 8>); break;
+  }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200enc_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, float eps,
                                  int rows, int d, void* out, long long ldo, float* stats, void* stream) {
   int rc = check_rows("b200enc_layernorm", x, ldx, rows, d);
@@ -27,12 +53,7 @@ extern "C" int b200enc_layernorm(const void* x, long long ldx, const float* gamm
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && ldo % 8 == 0 &&
                      (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0,
                  "b200enc_layernorm: out/gamma/beta must be 16-byte aligned");
-  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  layernorm_kernel<true><<<grid, LN_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, rows, d,
-      reinterpret_cast<__nv_bfloat16*>(out), ldo, reinterpret_cast<float2*>(stats));
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_layernorm<true>(x, ldx, gamma, beta, eps, rows, d, out, ldo, stats, stream);
 }
 
 extern "C" int b200enc_row_stats(const void* x, long long ldx, float eps, int rows, int d, float* stats,
@@ -40,12 +61,7 @@ extern "C" int b200enc_row_stats(const void* x, long long ldx, float eps, int ro
   int rc = check_rows("b200enc_row_stats", x, ldx, rows, d);
   if (rc) return rc;
   B200_CHECK_ARG(stats != nullptr, "b200enc_row_stats: null stats");
-  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  layernorm_kernel<false><<<grid, LN_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, nullptr, nullptr, eps, rows, d, nullptr, 0,
-      reinterpret_cast<float2*>(stats));
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_layernorm<false>(x, ldx, nullptr, nullptr, eps, rows, d, nullptr, 0, stats, stream);
 }
 
 extern "C" int b200enc_mean_tokens(const void* x, long long batch_stride, long long ldx, int B, int L, int d,
