@@ -1,10 +1,13 @@
 // C-ABI entry point for the attention core (see include/b200enc.h).
+#include <cstdlib>
+
 #include "../../include/b200enc.h"
 #ifdef ATT_V6
 #include "attention_v6.cuh"
 #else
 #include "attention.cuh"
 #include "attention_short.cuh"
+#include "attention_short_split.cuh"
 #endif
 #include "host_util.h"
 
@@ -92,6 +95,18 @@ static int attention_short_impl(const void* q, long long q_batch_stride, int ldq
 #endif
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   // the row length of ViT at 224 px (197 tokens -> 13 halves of 16 columns) has its own instantiation
+  static const bool use_split = [] {  // the two-threads-per-row instantiation for 197 keys (B200ENC_ATTN_SPLIT=0: off)
+    const char* e = getenv("B200ENC_ATTN_SPLIT");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (Lkv == ASP_LKV && use_split) {
+    CUtensorMap to2;
+    if ((rc = make_tmap_bf16(&to2, out, uint64_t(H) * ATT_HD, Lq, B, ldo, obs, 32, 32, 64))) return rc;
+    p.tm_o1 = p.tm_s1 + 8 * ASP_A;  // the hole between the two pieces of P (attention_short_split.cuh)
+    if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_short197_kernel), ATS_SMEM_BYTES))) return rc;
+    return launch_pdl(attention_short197_kernel, grid, ASP_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk,
+                      tv, to2, p);
+  }
   auto kern = p.nk16 == 208 ? attention_short_kernel<13> : attention_short_kernel<0>;
   if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), ATS_SMEM_BYTES))) return rc;
   return launch_pdl(kern, grid, ATT_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, to, p);

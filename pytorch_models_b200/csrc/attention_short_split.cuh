@@ -1,0 +1,399 @@
+// The 197-key instantiation of the short-sequence attention kernel with TWO threads per query row (sixteen softmax
+// warps, four per SM sub-partition instead of two): same pipeline, barriers, TMA stages and TMEM budget as
+// attention_short.cuh, which documents them; only what differs is described here.
+//
+// Why: in attention_short.cuh a sub-partition runs two softmax warps, one per query tile, and their busy phases
+// alternate: a single warp in its exponential phase reaches 9.6 clocks per column where two
+// overlapped warps reach 7.2, and pass 1 / the epilogue are dependent-latency chains of one warp. cuDNN's kernel on this
+// shape runs 16 warps per CTA. Here each row's 13 halves of 16 columns are split 7 : 6 between the two softmax
+// warpgroups of the tile (hsel = 0 / 1), which share the row's TMEM lane:
+//   * row maximum: each thread reduces its own halves, the pair exchanges the partial maxima through shared memory
+//     behind a named barrier (bar.sync, 64 threads: the two warps of the same tile and lane quarter);
+//   * P can no longer sit "in place from the start of S": thread B (halves 7..12) would overwrite columns of S that
+//     thread A (halves 0..6) has not read yet. Every MMA K step takes its own TMEM address for P, so P lives in two
+//     pieces, each at the start of its owner's column range: A's halves at columns [0, 56), B's at [120, 168) — a P half
+//     is only ever written over columns its own thread has already consumed. The columns in between, [56, 120), are the
+//     64 columns the aliased tile's O needs (TMEM layout for 176 < nk16 <= 208);
+//   * row sums come from the tensor core (P . 1, as in attention_short.cuh), so the pair exchanges nothing else;
+//   * output: each thread normalises 32 of the 64 columns of its row; every warp has its own 32-row x 64-byte staging
+//     buffer and its own TMA store (box 32 x 32), so the pair needs no second rendezvous.
+// 640 threads: control warpgroup (producer, issuer, watchdog, idle) + 4 softmax warpgroups; setmaxnreg 40 / 112.
+#pragma once
+#include "attention_short.cuh"
+
+namespace b200 {
+
+constexpr int ASP_THREADS = 640;
+constexpr int ASP_CONTROL_REGS = 40;
+constexpr int ASP_SOFTMAX_REGS = 112;  // 128 x 40 + 512 x 112 = 62464 <= 65536 (the kernel starts with 96 x 640)
+constexpr int ASP_NH = 13;             // 16-column halves of a 197-key row (nk16 = 208)
+constexpr int ASP_A = 7;               // halves of the first thread of a row; the second takes ASP_NH - ASP_A
+constexpr int ASP_LKV = 197;
+constexpr int ASP_P_B = 16 * ASP_A + 8;  // TMEM column (relative to S_t) of the second thread's first P half
+constexpr int ASP_STG_BYTES = 32 * 64;   // one warp's output rows: 32 x 32 bf16
+// the row-maximum exchange words live in the unused tail of stage 0's K slot (208 of 256 rows are loaded)
+constexpr int ASP_SMEM_XCH = ATS_OFF_K + 208 * 128;
+static_assert(ASP_SMEM_XCH + 2 * 2 * 128 * 4 <= ATS_OFF_V, "exchange words overflow the K slot");
+static_assert(16 * ASP_STG_BYTES <= 8 * ATT_STG_BYTES, "staging");
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(ASP_THREADS, 1)
+attention_short197_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                          const AttnShortParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + ATS_SMEM_BAR;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  constexpr int FULL = 0, EMPTY = 2, S_FULL = 4, P_FULL = 6, O_FULL = 8, T_FREE = 10, DONE = 12;
+  constexpr int kProtocolBarriers = 12;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATS_SMEM_BAR + 8 * 13);
+  const uint32_t progress_addr = sbase + ATS_SMEM_BAR + 8 * 13 + 4;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+#ifdef ATT_TRACE
+  int tr_n = 0;
+  const int tr_role = warp == 0 ? 0 : warp == 1 ? 1 : warp < 8 ? 2 : 3;
+#endif
+  unsigned int* const abw = p.abort_word;
+  if (sbase & 1023u) {
+    if (threadIdx.x == 0 && abw != nullptr) *reinterpret_cast<volatile unsigned int*>(abw) = 0xB200A117u;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(FULL + i), 1);
+      mbar_init(bar(EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1);
+      mbar_init(bar(P_FULL + i), 8);
+      mbar_init(bar(O_FULL + i), 1);
+      mbar_init(bar(T_FREE + i), 8);
+    }
+    mbar_init(bar(DONE), 18);  // producer, issuer, 16 softmax warps
+    *reinterpret_cast<volatile uint32_t*>(smem + ATS_SMEM_BAR + 8 * 13 + 4) = 0u;
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+  }
+  for (int i = threadIdx.x; i < 2048 / 4; i += ASP_THREADS) reinterpret_cast<uint32_t*>(smem + ATS_SMEM_ONES)[i] = 0x3f803f80u;
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int n_my = p.n_items > int(blockIdx.x) ? (p.n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  auto item_of = [&](int n) { return int(blockIdx.x) + n * int(gridDim.x); };
+  auto two_of = [&](int item) { return (p.n_qp == 1 ? 0 : item % p.n_qp) * 256 + ATT_BQ < p.Lq; };
+
+  if (warp < 4) setmaxnreg_dec<ASP_CONTROL_REGS>();
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (as attention_short.cuh)
+    for (int n = 0; n < n_my; ++n) {
+      const int item = item_of(n);
+      const int qp = p.n_qp == 1 ? 0 : item % p.n_qp;
+      const int bh = p.n_qp == 1 ? item : item / p.n_qp;
+      const int h = bh % p.H;
+      const int b = bh / p.H;
+      const bool two = two_of(item);
+      const uint32_t s = uint32_t(n) & 1u;
+      ATS_WAIT(bar(EMPTY + s), ((uint32_t(n) >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        const uint32_t st = sbase + s * ATS_STAGE_BYTES;
+        mbar_expect_tx(bar(FULL + s), (two ? 2 : 1) * ATT_TILE_BYTES + 2 * 208 * 128);
+        tma_load_3d(&tmQ, bar(FULL + s), st, h * ATT_HD, qp * 256, b);
+        if (two) tma_load_3d(&tmQ, bar(FULL + s), st + ATT_TILE_BYTES, h * ATT_HD, qp * 256 + ATT_BQ, b);
+        tma_load_3d(&tmK, bar(FULL + s), st + ATS_OFF_K, h * ATT_HD, 0, b);
+        tma_load_3d(&tmV, bar(FULL + s), st + ATS_OFF_V, h * ATT_HD, 0, b);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) mbar_arrive(bar(DONE));
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    uint32_t nq[2] = {0, 0};
+    uint32_t npv[2] = {0, 0};
+    uint32_t done = 0;
+    const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, 16 * ASP_NH, 0, 0);
+    const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
+    const uint32_t idesc_l = make_idesc_bf16(ATT_BQ, 16, 0, 0);
+    const uint64_t d_ones = make_smem_desc_sw128(sbase + ATS_SMEM_ONES, 16, 1024);
+    auto issue_qk = [&](int n, int t) {
+      const uint32_t st = sbase + (uint32_t(n) & 1u) * ATS_STAGE_BYTES;
+      if ((t == 0 ? p.alias0 : p.alias1) && nq[t] > 0) {
+        ATS_WAIT(bar(T_FREE + t), (nq[t] - 1) & 1u);
+        tc_fence_after();
+      }
+      const uint64_t dq = make_smem_desc_sw128(st + t * ATT_TILE_BYTES, 16, 1024);
+      const uint64_t dk = make_smem_desc_sw128(st + ATS_OFF_K, 16, 1024);
+      const bool drop_commit = p.debug_fault == 1 && blockIdx.x == 0 && n == 0 && t == 0;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k)
+          umma_ss(tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1), dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        if (!drop_commit) umma_commit(bar(S_FULL + t));
+      }
+      __syncwarp();
+      ++nq[t];
+      if (lane == 0) ATT_EV(100 + t);
+    };
+    auto issue_pv = [&](int n, int t) {
+      const uint32_t st = sbase + (uint32_t(n) & 1u) * ATS_STAGE_BYTES;
+      ATS_WAIT(bar(P_FULL + t), npv[t] & 1u);
+      if (lane == 0) ATT_EV(110 + t);
+      tc_fence_after();
+      const uint64_t dv0 = make_smem_desc_sw128(st + ATS_OFF_V, 16, 1024);
+      const uint32_t ps = tmem_base + (t == 0 ? p.tm_s0 : p.tm_s1);
+      const uint32_t d_o = tmem_base + (t == 0 ? p.tm_o0 : p.tm_o1);
+      const uint32_t d_l = tmem_base + (t == 0 ? p.tm_l0 : p.tm_l1);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ASP_NH; ++k) {
+          const uint32_t pa = ps + (k < ASP_A ? 8u * k : uint32_t(ASP_P_B) + 8u * (k - ASP_A));  // the two pieces of P
+          umma_ts(d_o, pa, dv0 + 128u * k, idesc_o, k != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < ASP_NH; ++k) {
+          const uint32_t pa = ps + (k < ASP_A ? 8u * k : uint32_t(ASP_P_B) + 8u * (k - ASP_A));
+          umma_ts(d_l, pa, d_ones + 2u * (k & 3), idesc_l, k != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(O_FULL + t));
+      }
+      __syncwarp();
+      ++npv[t];
+      if (lane == 0) ATT_EV(120 + t);
+    };
+    if (n_my > 0) {
+      ATS_WAIT(bar(FULL + 0), 0u);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (two_of(item_of(0))) issue_qk(0, 1);
+      for (int n = 0; n < n_my; ++n) {
+        const bool two = two_of(item_of(n));
+        const bool more = n + 1 < n_my;
+        issue_pv(n, 0);
+        if (more) {
+          ATS_WAIT(bar(FULL + ((uint32_t(n) + 1u) & 1u)), ((uint32_t(n) + 1u) >> 1) & 1u);
+          if (lane == 0) ATT_EV(130);
+          tc_fence_after();
+          issue_qk(n + 1, 0);
+        }
+        if (two) issue_pv(n, 1);
+        if (elect_one()) umma_commit(bar(EMPTY + (uint32_t(n) & 1u)));
+        __syncwarp();
+        if (more && two_of(item_of(n + 1))) issue_qk(n + 1, 1);
+        if (lane == 0) sts_u32_volatile(progress_addr, ++done);
+      }
+    }
+    if (lane == 0) mbar_arrive(bar(DONE));
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ watchdog (as attention_short.cuh)
+    if (abw != nullptr) {
+      uint32_t last = 0xFFFFFFFFu;
+      uint64_t t_last = 0;
+      bool raised = false;
+      while (!mbar_try_wait_hint(bar(DONE), 0u, 20000u)) {
+        const uint64_t now = global_timer_ns();
+        const uint32_t pr = lds_u32_volatile(progress_addr);
+        if (pr != last || t_last == 0) {
+          last = pr;
+          t_last = now;
+        } else if (now - t_last > B200_WAIT_LIMIT_NS) {
+          if (!raised && lane == 0) {
+            *reinterpret_cast<volatile unsigned int*>(abw) = 0xB200DEADu;
+            __threadfence_system();
+          }
+          raised = true;
+          if (lane < kProtocolBarriers) {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) mbar_arrive(bar(lane));
+          }
+          __nanosleep(2000);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax / output warpgroups
+    setmaxnreg_inc<ASP_SOFTMAX_REGS>();
+    const int wg = (warp - 4) >> 2;  // 0..3
+    const int t = wg >> 1;           // query tile
+    const int hsel = wg & 1;         // which column range of the row
+    const int qd = warp & 3;         // TMEM lane quarter
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + uint32_t(t == 0 ? p.tm_s0 : p.tm_s1) + lane_off;
+    const uint32_t tO = tmem_base + uint32_t(t == 0 ? p.tm_o0 : p.tm_o1) + lane_off + uint32_t(hsel * 32);
+    const uint32_t tL = tmem_base + uint32_t(t == 0 ? p.tm_l0 : p.tm_l1) + lane_off;
+    const uint32_t tSmine = tS + uint32_t(hsel ? 16 * ASP_A : 0);   // my first S half
+    const uint32_t tPmine = tS + uint32_t(hsel ? ASP_P_B : 0);      // my first P half
+    const int my_n = hsel ? ASP_NH - ASP_A : ASP_A;                 // my halves: 7 or 6 (warp-uniform)
+    const float c = p.scale_log2e;
+    const uint32_t stg_off = ATS_SMEM_STG + uint32_t(warp - 4) * ASP_STG_BYTES;
+    const bool alias = (t == 0 ? p.alias0 : p.alias1) != 0;
+    volatile float* xch = reinterpret_cast<volatile float*>(smem + ASP_SMEM_XCH);  // [tile][hsel][row]
+    const int row_in_tile = qd * 32 + lane;
+    const int bar_id = 1 + t * 4 + qd;  // named barrier of this (tile, lane quarter) pair of warps
+    uint32_t g = 0;
+    for (int n = 0; n < n_my; ++n) {
+      const int item = item_of(n);
+      const int qp = p.n_qp == 1 ? 0 : item % p.n_qp;
+      const int bh = p.n_qp == 1 ? item : item / p.n_qp;
+      const int h = bh % p.H;
+      const int b = bh / p.H;
+      const int row0 = qp * 256 + t * ATT_BQ;
+      if (row0 >= p.Lq) continue;
+      const bool warp_live = row0 + qd * 32 < p.Lq;  // the same for both warps of a pair
+      ATS_WAIT(bar(S_FULL + t), g & 1u);
+      if (lane == 0 && qd == 0 && hsel == 0) ATT_EV(200 + t);
+      tc_fence_after();
+      if (warp_live) {
+        // ---- pass 1: maximum of my halves (all seven / six loads in flight, one wait), exchange with my partner
+        uint32_t u[4][16];
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        auto mask_tail = [&](uint32_t(&v)[16], int k) {  // the row's last half holds the columns >= 197
+          if (hsel && k == ASP_NH - ASP_A - 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (16 * (ASP_NH - 1) + i >= ASP_LKV) v[i] = 0xff800000u;
+          }
+        };
+        auto max_half = [&](uint32_t(&v)[16], int k) {
+          mask_tail(v, k);
+          mx0 = fmax3(mx0, __uint_as_float(v[0]), __uint_as_float(v[1]));
+          mx1 = fmax3(mx1, __uint_as_float(v[2]), __uint_as_float(v[3]));
+          mx2 = fmax3(mx2, __uint_as_float(v[4]), __uint_as_float(v[5]));
+          mx3 = fmax3(mx3, __uint_as_float(v[6]), __uint_as_float(v[7]));
+          mx0 = fmax3(mx0, __uint_as_float(v[8]), __uint_as_float(v[9]));
+          mx1 = fmax3(mx1, __uint_as_float(v[10]), __uint_as_float(v[11]));
+          mx2 = fmax3(mx2, __uint_as_float(v[12]), __uint_as_float(v[13]));
+          mx3 = fmax3(mx3, __uint_as_float(v[14]), __uint_as_float(v[15]));
+        };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_ld16(tSmine + 16 * k, u[k]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) max_half(u[k], k);
+        tmem_ld16(tSmine + 16 * 4, u[0]);
+        tmem_ld16(tSmine + 16 * 5, u[1]);
+        if (6 < my_n) tmem_ld16(tSmine + 16 * 6, u[2]);
+        tmem_wait_ld();
+        max_half(u[0], 4);
+        max_half(u[1], 5);
+        if (6 < my_n) max_half(u[2], 6);
+        const float m_part = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        xch[(t * 2 + hsel) * 128 + row_in_tile] = m_part;
+        // pass 2 starts with halves 0 and 1 again: have them on their way before the rendezvous
+        tmem_ld16(tSmine, u[0]);
+        tmem_ld16(tSmine + 16, u[1]);
+        named_bar_sync(bar_id, 64);
+        const float m = fmaxf(m_part, xch[(t * 2 + (hsel ^ 1)) * 128 + row_in_tile]);
+        const float m_off = m == -INFINITY ? 0.0f : m;
+        const float2 c2 = make_float2(c, c);
+        const float2 nmc2 = make_float2(-m_off * c, -m_off * c);
+        if (lane == 0 && qd == 0 && hsel == 0) ATT_EV(202 + t);
+        // ---- pass 2: exponentials of my halves, P into my piece
+        auto exp_half = [&](uint32_t(&v)[16], int k) {
+          mask_tail(v, k);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 e = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, nmc2);
+#if ATT_POLY_EVERY > 0
+            const float2 pr = (i % ATT_POLY_EVERY) == ATT_POLY_EVERY - 1 ? exp2_poly2(e)
+                                                                         : make_float2(fast_exp2(e.x), fast_exp2(e.y));
+#else
+            const float2 pr = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+#endif
+            pk[i] = pack_bf16x2(pr.x, pr.y);
+          }
+          tmem_st8(tPmine + 8 * k, pk);
+        };
+        tmem_wait_ld();
+        tmem_ld16(tSmine + 16 * 2, u[2]);
+        tmem_ld16(tSmine + 16 * 3, u[3]);
+        exp_half(u[0], 0);
+        exp_half(u[1], 1);
+        tmem_wait_ld();
+        tmem_ld16(tSmine + 16 * 4, u[0]);
+        tmem_ld16(tSmine + 16 * 5, u[1]);
+        exp_half(u[2], 2);
+        exp_half(u[3], 3);
+        tmem_wait_ld();
+        if (6 < my_n) tmem_ld16(tSmine + 16 * 6, u[2]);
+        exp_half(u[0], 4);
+        exp_half(u[1], 5);
+        if (6 < my_n) {
+          tmem_wait_ld();
+          exp_half(u[2], 6);
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(P_FULL + t));
+      if (lane == 0 && qd == 0 && hsel == 0) ATT_EV(210 + t);
+      ATS_WAIT(bar(O_FULL + t), g & 1u);
+      tc_fence_after();
+      if (lane == 0 && qd == 0 && hsel == 0) ATT_EV(220 + t);
+      if (warp_live) {
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        const uint32_t lsum = tmem_ld1(tL);
+        if (elect_one()) tma_store_wait_read<0>();
+        __syncwarp();
+        tmem_wait_ld();
+        if (alias) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(T_FREE + t));
+        }
+        const float inv = 1.0f / __uint_as_float(lsum);
+        uint8_t* dst = smem + stg_off + lane * 64;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + ((i ^ ((lane >> 1) & 3)) << 4)) = w;  // 64B swizzle of the store's tensor map
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_3d(&tmO, sbase + stg_off, h * ATT_HD + hsel * 32, row0 + qd * 32, b);
+          tma_store_commit();
+        }
+        __syncwarp();
+      } else if (alias) {
+        if (lane == 0) mbar_arrive(bar(T_FREE + t));
+      }
+      tc_fence_before();
+      if (lane == 0 && qd == 0 && hsel == 0) ATT_EV(230 + t);
+      ++g;
+    }
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DONE));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b200
