@@ -203,6 +203,42 @@ int b200enc_time_rows(const void* x, int dtype, int N, int C, int T, void* rows,
 int b200enc_whisper_logmel(const float* audio, long long audio_stride, int N, int L, const float* filters_t, int n_mels,
                            float* out, int* sample_max, void* stream);
 
+/*
+ * Launch plan: a recorded sequence of the entry points above, enqueued by ONE call.
+ *
+ * The reference's forward is a Python loop over modules (nn.Sequential at transformer.py:133-149, the layer body at
+ * :122-130); the drop-in modules of this package used to make one ctypes call per kernel from the same kind of loop,
+ * which costs ~29 us of interpreter time per launch (1.9 ms for the 65 launches of a ViT-B/16 forward). A model
+ * records its launches once per (input shape, weights) — every argument of every call, workspaces included — and
+ * replays the array; only the input / output pointers are patched by the host between replays. Each element names
+ * an entry point (`kind`) and carries its arguments in declaration order: the struct for the two GEMM entry points,
+ * pointer arguments in p[], integer arguments (int / long long) in i[], float arguments in f[]. The calls are
+ * made in order on `stream`, with the same validation and error behaviour as the individual entry points; on a
+ * non-zero return *failed_op (if not NULL) is the index of the element that failed and nothing after it was enqueued.
+ */
+#define B200ENC_OP_LINEAR 1
+#define B200ENC_OP_PATCH_EMBED16 2   /* i[0] = img_h, i[1] = img_w */
+#define B200ENC_OP_ATTENTION 3
+#define B200ENC_OP_ATTENTION_BIAS 4
+#define B200ENC_OP_LAYERNORM 5
+#define B200ENC_OP_ROW_STATS 6
+#define B200ENC_OP_MEAN_TOKENS 7
+#define B200ENC_OP_PATCH_ROWS 8
+#define B200ENC_OP_CLS_ROWS 9
+#define B200ENC_OP_EMBED_ROWS 10
+#define B200ENC_OP_TIME_ROWS 11
+
+typedef struct b200enc_op {
+  int kind;                    /* B200ENC_OP_* */
+  int reserved;
+  b200enc_linear_args linear;  /* B200ENC_OP_LINEAR, B200ENC_OP_PATCH_EMBED16 */
+  const void* p[8];
+  long long i[16];
+  float f[2];
+} b200enc_op;
+
+int b200enc_run_ops(const b200enc_op* ops, int n_ops, int* failed_op, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

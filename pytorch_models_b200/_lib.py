@@ -44,6 +44,23 @@ class LinearArgs(ctypes.Structure):
     ]
 
 
+class Op(ctypes.Structure):
+    """Mirror of ``b200enc_op`` in include/b200enc.h: one recorded launch of a plan (`plans.py`)."""
+
+    _fields_ = [
+        ("kind", c_int), ("reserved", c_int),
+        ("linear", LinearArgs),
+        ("p", c_void_p * 8), ("i", c_longlong * 16), ("f", c_float * 2),
+    ]
+
+
+# b200enc_op.kind per entry point (B200ENC_OP_* in include/b200enc.h)
+OP_KINDS = {
+    "b200enc_linear": 1, "b200enc_patch_embed16": 2, "b200enc_attention": 3, "b200enc_attention_bias": 4,
+    "b200enc_layernorm": 5, "b200enc_row_stats": 6, "b200enc_mean_tokens": 7, "b200enc_patch_rows": 8,
+    "b200enc_cls_rows": 9, "b200enc_embed_rows": 10, "b200enc_time_rows": 11,
+}
+
 _SIGNATURES = {
     "b200enc_version": (c_int, []),
     "b200enc_last_error": (ctypes.c_char_p, []),
@@ -75,6 +92,7 @@ _SIGNATURES = {
     "b200enc_whisper_logmel": (
         c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200enc_time_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200enc_run_ops": (c_int, [ctypes.POINTER(Op), c_int, ctypes.POINTER(c_int), c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -90,6 +90,14 @@ struct AttnParams {
 #ifndef ATT_POLY_EVERY
 #define ATT_POLY_EVERY 4
 #endif
+#ifndef ATT_MAX_CHAINS
+#define ATT_MAX_CHAINS 2  // dependent chains of the row maximum: 2 = round-1 form, 4 / 8 = FMNMX3 chains + tree
+#endif
+__device__ __forceinline__ float att_fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 // 2^x for x <= ~8 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], max relative error
 // 7.7e-5, far below the bf16 rounding of P): takes a share of the exponentials off the MUFU pipe.
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
@@ -138,6 +146,29 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
       for (int i = 0; i < 32; ++i)
         if (ch * 32 + i >= lim) v[ch][i] = 0xff800000u;
   }
+#if ATT_MAX_CHAINS > 2
+  // ATT_MAX_CHAINS independent chains of three-input maxima (FMNMX3: two scores per instruction) and a short tree:
+  // the two-chain form below is bound by the latency of 64 dependent FMNMX per chain (csrc/microbench2.cu: 148 clocks
+  // per block against 31-52 for eight chains)
+  float mx[ATT_MAX_CHAINS];
+#pragma unroll
+  for (int q = 0; q < ATT_MAX_CHAINS; ++q) mx[q] = -INFINITY;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (ch < n_chunks) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2 * ATT_MAX_CHAINS)
+#pragma unroll
+        for (int q = 0; q < ATT_MAX_CHAINS; ++q)
+          mx[q] = att_fmax3(mx[q], __uint_as_float(v[ch][i + 2 * q]), __uint_as_float(v[ch][i + 2 * q + 1]));
+    }
+  }
+#pragma unroll
+  for (int w = ATT_MAX_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+    for (int q = 0; q < w; ++q) mx[q] = fmaxf(mx[q], mx[q + w]);
+  const float m_new = fmaxf(m, mx[0]);
+#else
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
@@ -150,6 +181,7 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, int n_chunks, bool ma
     }
   }
   const float m_new = fmaxf(m, fmaxf(mx0, mx1));
+#endif
   // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
   // the first block, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);

@@ -6,6 +6,7 @@ current stream, and call into the library. No arithmetic happens in PyTorch here
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 from torch import Tensor
@@ -15,6 +16,7 @@ from . import _lib
 
 LAUNCHES = 0  # kernels launched through the C-ABI by this process (every entry point launches exactly one)
 _PROFILE: list | None = None  # when a list: (entry point, meta, start event, end event) per launch
+_RECORD = None  # plans._Recorder while a forward is being recorded into a launch plan (plans.py), else None
 
 
 def profile(enable: bool) -> list | None:
@@ -34,6 +36,12 @@ def _call(name: str, meta: dict | None, dev: torch.device, *args) -> None:
             return _call(name, meta, dev, *args)
     fn = getattr(_lib.load(), name)
     stream = torch.cuda.current_stream(dev)
+    plan_rec = _RECORD
+    if plan_rec is not None and plan_rec.thread == threading.get_ident():
+        if name in _lib.OP_KINDS:
+            plan_rec.calls.append((name, args))
+        else:
+            plan_rec.ok = False  # an entry point b200enc_run_ops cannot replay: this forward stays on the per-call path
     rec = _PROFILE
     if rec is None:
         rc = fn(*args, stream.cuda_stream)
@@ -68,6 +76,8 @@ def _need_cuda(*ts: Tensor | None) -> torch.device:
             raise RuntimeError(f"tensors of one kernel call live on different devices ({dev} and {t.device})")
     if dev is None:
         raise RuntimeError("no tensor arguments")
+    if _RECORD is not None:  # a launch plan keeps every tensor its launches touch alive (plans.py)
+        _RECORD.keep.extend(t for t in ts if t is not None)
     return dev
 
 

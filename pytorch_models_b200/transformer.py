@@ -29,7 +29,7 @@ from types import SimpleNamespace
 import torch
 from torch import Tensor, nn
 
-from . import ops
+from . import ops, plans
 from .compile import compilable, compilable_module
 
 _SUPPORTED_HEAD_DIM = 64
@@ -50,6 +50,7 @@ def invalidate_packed() -> None:
     this function — otherwise the forward keeps using the stale bf16 copies, silently."""
     global _PACK_EPOCH
     _PACK_EPOCH += 1
+    plans.invalidate_all()  # recorded launch plans hold pointers to the packed copies
 
 
 def _version(p: Tensor) -> int:
@@ -549,7 +550,9 @@ class Encoder(nn.Sequential):
     @compilable(lambda self, x, extra: (x.shape, x.dtype))
     def forward(self, x: Tensor) -> Tensor:
         x3, meta = _as_tokens(x, self.d_model)
-        return _restore(self.run(x3), meta)
+        if len(self) == 0 or x3.numel() == 0:
+            return _restore(self.run(x3), meta)
+        return _restore(plans.run(self, (x3,), self.run), meta)  # recorded once, replayed by one C-ABI call
 
 
 def partial_stats_of(row: Tensor) -> Tensor:
@@ -622,7 +625,9 @@ class Decoder(nn.ModuleList):
         m3 = None
         if memory is not None and len(self) and self[0].ca is not None:
             m3, _ = _as_tokens(memory, self.d_model)
-        return _restore(self.run(x3, m3), meta)
+        if len(self) == 0 or x3.numel() == 0:
+            return _restore(self.run(x3, m3), meta)
+        return _restore(plans.run(self, (x3,) if m3 is None else (x3, m3), self.run), meta)
 
 
 # ----------------------------------------------------------------------------------------------- language-model ends
