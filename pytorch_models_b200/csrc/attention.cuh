@@ -90,6 +90,9 @@ struct AttnParams {
 #ifndef ATT_POLY_EVERY
 #define ATT_POLY_EVERY 4
 #endif
+#ifndef ATT_FUSED_ISSUE
+#define ATT_FUSED_ISSUE 1  // MMA issuer: 1 = P.V(j) + Q.K(j+1) of a tile as one run behind the P_FULL wait (round 2)
+#endif
 #ifndef ATT_MAX_CHAINS
 #define ATT_MAX_CHAINS 2  // dependent chains of the row maximum: 2 = round-1 form, 4 / 8 = FMNMX3 chains + tree
 #endif
@@ -428,6 +431,66 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
 
       Blk cur{int(blockIdx.x), 0, 0u, 0u, 0u, 0, 0};
+#if ATT_FUSED_ISSUE
+      // Round 2 (event trace at L = 1500, profiles/r02/trace_attn_l1500.md): between a tile publishing P(j) and its
+      // next scores S(j+1) arriving lay ~1500-1900 clocks of which only ~610 were tcgen05.mma issue — the rest was
+      // this warp's own serial work AFTER the wake-up (operand-barrier waits for the next block, descriptor
+      // construction, two elect / commit / __syncwarp rounds). Everything that does not depend on P is therefore
+      // done BEFORE the P_FULL wait, and P.V(j) and Q.K(j+1) of a tile go out as one run of twelve MMAs from one
+      // elected region.
+      if (cur.item < p.n_items) {
+        set_item(cur);
+        start_block(cur, 0, 1);
+        while (true) {
+          const Blk nxt = advance(cur);
+          const bool more = nxt.item < p.n_items;
+          if (more) {  // operands of the next block: loaded long ago (3-stage ring), the wait is off the critical path
+            if (nxt.j == 0) mbar_wait_plain(bar(Q_FULL + (nxt.it & 1u)), (nxt.it >> 1) & 1u);
+            mbar_wait_plain(bar(KV_FULL + nxt.stage), nxt.phase);
+          }
+          const uint64_t dv0 = make_smem_desc_sw128(sbase + ATT_SMEM_V + cur.stage * ATT_TILE_BYTES, 16, 1024);
+          const uint64_t dk0 = make_smem_desc_sw128(sbase + ATT_SMEM_K + nxt.stage * ATT_TILE_BYTES, 16, 1024);
+          const uint32_t sq_n = sbase + ATT_SMEM_Q + (nxt.it & 1u) * 2 * ATT_TILE_BYTES;
+          const int ksteps = n_mma_of(cur.j) / 16;
+          const uint32_t acc0 = cur.j > 0 ? 1u : 0u;
+          const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, more ? n_mma_of(nxt.j) : ATT_BKV, 0, 0);
+          const bool q_done = more && nxt.j == max(nxt.nb0, nxt.nb1) - 1;  // last block that reads nxt's Q tiles
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const bool pv = active(cur, t);
+            const bool qk = more && active(nxt, t);
+            const uint64_t dq = make_smem_desc_sw128(sq_n + t * ATT_TILE_BYTES, 16, 1024);
+            const uint32_t tS = tmem_base + t * 256;
+            if (pv) mbar_wait_plain(bar(P_FULL + t), g[t] & 1u);
+            if (lane == 0) ATT_EV(110 + t);
+            tc_fence_after();
+            if (elect_one()) {
+              if (pv) {
+#pragma unroll
+                for (int k = 0; k < ATT_BKV / 16; ++k)
+                  if (k < ksteps) umma_ts(tS + 128, tS + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : acc0);
+                umma_commit(bar(O_FULL + t));
+              }
+              if (qk) {
+#pragma unroll
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, dq + 2u * k, dk0 + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(bar(S_FULL + t));
+              }
+              if (t == 1) {
+                if (q_done) umma_commit(bar(Q_EMPTY + (nxt.it & 1u)));
+                umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
+              }
+            }
+            __syncwarp();
+            if (lane == 0) ATT_EV(120 + t);
+            if (pv) ++g[t];
+          }
+          if (lane == 0) sts_u32_volatile(progress_addr, ++blocks_done);  // the watchdog's sign of life
+          if (!more) break;
+          cur = nxt;
+        }
+      }
+#else
       if (cur.item < p.n_items) {
         set_item(cur);
         start_block(cur, 0, 1);
@@ -445,6 +508,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           cur = nxt;
         }
       }
+#endif
       if (lane == 0) mbar_arrive(bar(DONE));
     }
   } else if (warp == 2) {

@@ -63,6 +63,9 @@ struct AttnShortParams {
   long long* trace;
 };
 
+#ifndef ATS_FUSED_ISSUE
+#define ATS_FUSED_ISSUE 0  // 1: P.V(n) + row sums + Q.K(n+1) of tile 0 as one run behind the P_FULL wait (measured 6 % SLOWER at L = 197: 0.267 vs 0.251 ms)
+#endif
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -215,12 +218,49 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int n = 0; n < n_my; ++n) {
         const bool two = two_of(item_of(n));
         const bool more = n + 1 < n_my;
-        issue_pv(n, 0);
-        if (more) {
-          ATS_WAIT(bar(FULL + ((uint32_t(n) + 1u) & 1u)), ((uint32_t(n) + 1u) >> 1) & 1u);
-          if (lane == 0) ATT_EV(130);
+#if ATS_FUSED_ISSUE
+        // Tile 0 with private O columns (no T_FREE hand-shake): when the next item's operands have already landed —
+        // probed BEFORE the P_FULL wait — P.V(n), the row sums and Q.K(n+1) leave as one run of MMAs from one elected
+        // region, with every descriptor built ahead of the wake-up (the trace showed more clocks in this warp's
+        // serial work between the groups than in the MMA issue itself; same change as in attention.cuh).
+        const uint32_t fb = bar(FULL + ((uint32_t(n) + 1u) & 1u)), fpar = ((uint32_t(n) + 1u) >> 1) & 1u;
+        const bool fuse0 = more && !p.alias0 && __all_sync(0xffffffffu, mbar_try_wait(fb, fpar));
+        if (fuse0) {
+          const uint32_t st = sbase + (uint32_t(n) & 1u) * ATS_STAGE_BYTES;
+          const uint32_t stn = sbase + ((uint32_t(n) + 1u) & 1u) * ATS_STAGE_BYTES;
+          const uint64_t dv0 = make_smem_desc_sw128(st + ATS_OFF_V, 16, 1024);
+          const uint64_t dq = make_smem_desc_sw128(stn, 16, 1024);
+          const uint64_t dk = make_smem_desc_sw128(stn + ATS_OFF_K, 16, 1024);
+          const uint32_t pa0 = tmem_base + p.tm_s0, d_o = tmem_base + p.tm_o0, d_l = tmem_base + p.tm_l0;
+          ATS_WAIT(bar(P_FULL + 0), npv[0] & 1u);
+          if (lane == 0) ATT_EV(110);
           tc_fence_after();
-          issue_qk(n + 1, 0);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < ATS_MAX_KV / 16; ++k)
+              if (k < ksteps) umma_ts(d_o, pa0 + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < ATS_MAX_KV / 16; ++k)
+              if (k < ksteps) umma_ts(d_l, pa0 + 8u * k, d_ones + 2u * (k & 3), idesc_l, k != 0 ? 1u : 0u);
+            umma_commit(bar(O_FULL + 0));
+#pragma unroll
+            for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(pa0, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(bar(S_FULL + 0));
+          }
+          __syncwarp();
+          ++npv[0];
+          ++nq[0];
+          if (lane == 0) ATT_EV(100);
+        } else
+#endif
+        {
+          issue_pv(n, 0);
+          if (more) {
+            ATS_WAIT(bar(FULL + ((uint32_t(n) + 1u) & 1u)), ((uint32_t(n) + 1u) >> 1) & 1u);
+            if (lane == 0) ATT_EV(130);
+            tc_fence_after();
+            issue_qk(n + 1, 0);
+          }
         }
         if (two) issue_pv(n, 1);
         if (elect_one()) umma_commit(bar(EMPTY + (uint32_t(n) & 1u)));  // every MMA reading this stage has been issued

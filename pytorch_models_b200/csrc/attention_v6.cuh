@@ -31,6 +31,17 @@ constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_THREADS = 384;  // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1, 2: softmax
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
+#ifndef ATT_V6_PLAIN
+#define ATT_V6_PLAIN 0  // 1: the softmax warps spin on their barriers without the bound (A/B of what the bound costs)
+#endif
+#if ATT_V6_PLAIN
+#define V6_WAIT(b, par, ctx) mbar_wait_plain(b, par)
+#else
+#define V6_WAIT(b, par, ctx) mbar_wait(b, par, ctx)
+#endif
+#ifndef ATT_V6_LEAN
+#define ATT_V6_LEAN 1  // MMA issuer: 1 = hoisted waits + three elected regions per block (see the issuer), 0 = first form
+#endif
 #ifndef ATT_MMA_ORDER
 #define ATT_MMA_ORDER 0  // 0: PV0 PV1 QK0 QK1 per block (shipped); 1: PV0 QK0 PV1 QK1 (measured slower at L=197)
 #endif
@@ -250,7 +261,7 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
       if (ch == 0 && sy.o_parity >= 0) {
         // P.V of the previous block has finished: P's columns are free and O is complete. It was issued a whole
         // block ago; the wait sits here, after the first chunk's exponentials, so that its latency is covered.
-              mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), *sy.wait);
+              V6_WAIT(sy.bar_o_full, uint32_t(sy.o_parity), *sy.wait);
               tc_fence_after();
             }
       tmem_st16(tP + ch * 16, pk);
@@ -467,6 +478,85 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
 
       Blk cur{int(blockIdx.x), 0, 0u, 0u, 0u, 0, 0};
+#if ATT_V6_LEAN
+      // Lean issue loop (round 2, second session). The event trace of the shipped kernel showed that this warp, not the
+      // softmax warps, set the period: ~1000 clocks of its own serial work per (tile, block) around ~600 clocks of
+      // tcgen05.mma issue. Here everything that does not depend on the softmax warps (operand barriers of block n+2,
+      // descriptors) happens BEFORE the P_FULL wait; per block there are three elected regions: P.V(n) of tile 0,
+      // P.V(n) of tile 1, and the score MMAs of block n+2 for both tiles together with every commit of the block.
+      if (cur.item < p.n_items) {
+        set_item(cur);
+        start_block(cur, 0, 1);
+        Blk nx1 = advance(cur);
+        bool have1 = nx1.item < p.n_items;
+        if (have1) start_block(nx1, 0, 1);
+        while (true) {
+          Blk nx2 = nx1;
+          bool have2 = false;
+          if (have1) {
+            nx2 = advance(nx1);
+            have2 = nx2.item < p.n_items;
+          }
+          if (have2) {  // loaded long ago (4-stage ring): off the critical path
+            if (nx2.j == 0) mbar_wait_plain(bar(Q_FULL + (nx2.it & 1u)), (nx2.it >> 1) & 1u);
+            mbar_wait_plain(bar(KV_FULL + nx2.stage), nx2.phase);
+          }
+          const uint64_t dv0 = make_smem_desc_sw128(sbase + ATT_SMEM_V + cur.stage * ATT_TILE_BYTES, 16, 1024);
+          const uint64_t dk0 = make_smem_desc_sw128(sbase + ATT_SMEM_K + nx2.stage * ATT_TILE_BYTES, 16, 1024);
+          const uint32_t sq_n = sbase + ATT_SMEM_Q + (nx2.it & 1u) * 2 * ATT_TILE_BYTES;
+          const uint64_t dq0 = make_smem_desc_sw128(sq_n, 16, 1024);
+          const uint64_t dq1 = make_smem_desc_sw128(sq_n + ATT_TILE_BYTES, 16, 1024);
+          const int ksteps = n_mma_of(cur.j) / 16;
+          const uint32_t acc0 = cur.j > 0 ? 1u : 0u;
+          const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, have2 ? n_mma_of(nx2.j) : ATT_BKV, 0, 0);
+          const bool q_done = have2 && nx2.j == max(nx2.nb0, nx2.nb1) - 1;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (!active(cur, t)) continue;
+            const uint32_t tT = tmem_base + t * ATT_TM_TILE;
+            mbar_wait_plain(bar(P_FULL + t), npv[t] & 1u);
+            if (lane == 0) ATT_EV(110 + t);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < ATT_BKV / 16; ++k)
+                if (k < ksteps) umma_ts(tT + ATT_TM_O, tT + ATT_TM_P + 8u * k, dv0 + 128u * k, idesc_o, k != 0 ? 1u : acc0);
+              umma_commit(bar(O_FULL + t));
+            }
+            __syncwarp();
+            if (lane == 0) ATT_EV(120 + t);
+            ++npv[t];
+          }
+          const bool qk0 = have2 && active(nx2, 0), qk1 = have2 && active(nx2, 1);
+          if (qk0 && nqk[0] > 0) mbar_wait_plain(bar(S_EMPTY + 0), (nqk[0] - 1) & 1u);
+          if (qk1 && nqk[1] > 0) mbar_wait_plain(bar(S_EMPTY + 1), (nqk[1] - 1) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            if (qk0) {
+#pragma unroll
+              for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tmem_base, dq0 + 2u * k, dk0 + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+              umma_commit(bar(S_FULL + 0));
+            }
+            if (qk1) {
+#pragma unroll
+              for (int k = 0; k < ATT_HD / 16; ++k)
+                umma_ss(tmem_base + ATT_TM_TILE, dq1 + 2u * k, dk0 + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+              umma_commit(bar(S_FULL + 1));
+            }
+            if (q_done) umma_commit(bar(Q_EMPTY + (nx2.it & 1u)));
+            umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
+          }
+          __syncwarp();
+          if (lane == 0) ATT_EV(100);
+          if (qk0) ++nqk[0];
+          if (qk1) ++nqk[1];
+          if (!have1) break;
+          cur = nx1;
+          nx1 = nx2;
+          have1 = have2;
+        }
+      }
+#else
       if (cur.item < p.n_items) {
         set_item(cur);
         start_block(cur, 0, 1);
@@ -502,6 +592,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           have1 = have2;
         }
       }
+#endif
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / output warpgroups
@@ -546,7 +637,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // columns of this block this row may attend to: all valid ones, or up to the diagonal with a causal mask
         const bool diag = p.causal && j * ATT_BKV + ATT_BKV - 1 > row0;  // warp-uniform
         const int lim = diag ? min(nvalid, qrow - j * ATT_BKV + 1) : nvalid;
-        mbar_wait(bar(S_FULL + t), g & 1u, wctx);
+        V6_WAIT(bar(S_FULL + t), g & 1u, wctx);
         if (lane == 0 && qd == 2) ATT_EV(200 + t);
         tc_fence_after();
         float alpha = 1.0f;
@@ -588,7 +679,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sy.bar_s_empty);
-          if (sy.o_parity >= 0) mbar_wait(sy.bar_o_full, uint32_t(sy.o_parity), wctx);
+          if (sy.o_parity >= 0) V6_WAIT(sy.bar_o_full, uint32_t(sy.o_parity), wctx);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -596,7 +687,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
         if (lane == 0 && qd == 2) ATT_EV(210 + t);
       }
-      mbar_wait(bar(O_FULL + t), (g - 1) & 1u, wctx);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
+      V6_WAIT(bar(O_FULL + t), (g - 1) & 1u, wctx);  // cannot be lapped: the next flip needs this warp's next P_FULL arrive
       tc_fence_after();
       if (lane == 0 && qd == 2) ATT_EV(220 + t);
       // normalise the 64 output columns of this head and hand the warp's 32 rows to one TMA store (rows >= Lq are

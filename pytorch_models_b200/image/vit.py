@@ -53,10 +53,10 @@ class MHAPooling(nn.Module):
         self.mlp = MLP(d_model, int(d_model * mlp_ratio))
 
     def forward(self, x: Tensor) -> Tensor:
-        pooled = self.attn(self.probe, x).squeeze(1)  # (N, d)
-        if pooled.dtype != torch.bfloat16:
-            pooled = pooled.to(torch.bfloat16)
-        pooled = pooled.contiguous()
+        if x.dtype != torch.bfloat16 or not x.is_contiguous():
+            x = x.to(torch.bfloat16).contiguous()
+        probe = self.probe.detach().to(torch.bfloat16).contiguous()  # parameter-derived (plan-safe)
+        pooled = self.attn.run(probe, x).squeeze(1)  # (N, d) bf16: library launches only, no dtype round trip
         N, d = pooled.shape
         # x + mlp(norm(x)) with the LayerNorm folded into linear1 (vit.py:42)
         self.mlp.check_supported()

@@ -204,9 +204,19 @@ class MHA(nn.Module):
         causal: bool = False,
     ) -> Tensor:
         self.check_supported(attn_bias, causal)
+        q3, meta = _as_tokens(q, self.q_proj.in_features)
+        out = self.run(q3, k, v, attn_bias, causal)
+        if out.shape[0] != q3.shape[0]:
+            meta = ((out.shape[0],), meta[1])
+        return _restore(out, meta)
+
+    def run(self, q3: Tensor, k: Tensor | None = None, v: Tensor | None = None, attn_bias: Tensor | None = None,
+            causal: bool = False) -> Tensor:
+        """`forward` on kernel-ready tokens: q3 bf16 contiguous (B, Lq, d) -> bf16 (B, Lq, d_out), no dtype round trip
+        (what `MHAPooling` calls, so that the pooling head consists of library launches only)."""
+        self.check_supported(attn_bias, causal)
         d_in = self.q_proj.in_features
         inner = self.n_heads * self.head_dim
-        q3, meta = _as_tokens(q, d_in)
         B, Lq, _ = q3.shape
         dev = q3.device
         if k is None and v is None:
@@ -215,7 +225,7 @@ class MHA(nn.Module):
             ops.linear(q3.view(B * Lq, d_in), pk.w, pk.bias, qkv.view(B * Lq, 3 * inner))
             qv, kv_k, kv_v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
         else:
-            k = q if k is None else k
+            k = q3 if k is None else k
             k3, _ = _as_tokens(k, d_in)
             Bk, Lkv, _ = k3.shape
             pq = self._pack("q", [self.q_proj])
@@ -242,9 +252,7 @@ class MHA(nn.Module):
         po = self._pack("out", [self.out_proj])
         out = torch.empty(B, Lq, self.out_proj.out_features, device=dev, dtype=torch.bfloat16)
         ops.linear(att.view(B * Lq, inner), po.w, po.bias, out.view(B * Lq, -1))
-        if B != q3.shape[0]:
-            meta = ((B,), meta[1])
-        return _restore(out, meta)
+        return out
 
 
 _ACTS = dict(

@@ -38,6 +38,12 @@ with torch.no_grad():
     gpu_ms, cpu_ms = timeit(lambda: m(x))
     print(f"launch plan (one b200enc_run_ops call): {gpu_ms:.3f} ms/step GPU, CPU enqueue time {cpu_ms:.3f} ms/step; "
           f"stats {plans.STATS}; output equals per-launch path: {torch.equal(m(x), y_calls)}")
+    for iters in (8, 14, 20, 40):  # launches in flight: does a deep launch queue (CPU far ahead) cost GPU time?
+        plans.enable(False)
+        g0, c0 = timeit(lambda: m(x), iters=iters)
+        plans.enable(True)
+        g1, c1 = timeit(lambda: m(x), iters=iters)
+        print(f"  {iters} forwards in flight: per-launch {g0:.3f} ms GPU / {c0:.3f} ms CPU, plan {g1:.3f} ms GPU / {c1:.3f} ms CPU")
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
