@@ -239,6 +239,10 @@ def main() -> None:
                          "weak: every GPU takes the whole configured batch")
     ap.add_argument("--chunk", type=int, default=0,
                     help="images per H2D/compute pipeline chunk in the e2e leg (0 = the whole per-GPU batch)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="device-rate loop: replay the forward as one CUDA graph (graphs.GraphedForward). auto = when the "
+                         "per-GPU batch is at most 256 images (the strong-scaled shards), where 64 stream launches "
+                         "cost the GPU ~7 %% more than one graph launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -288,21 +292,28 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and B <= 256)
+
     def device_rate(batch: int, n_steps: int, seed: int, sample_clocks: bool):
         """K forwards over a device-resident batch, CUDA events on the launching stream, barrier + synchronize on both
         sides, max over ranks. Returns (ms per step, launches, clocks, last output, the batch)."""
         torch.manual_seed(seed + rank)
         xd = torch.randn(batch, *cfg["shape"], device=dev).bfloat16()
+        fwd = model
+        if use_graph and batch == B:
+            from pytorch_models_b200.graphs import GraphedForward
+
+            fwd = GraphedForward(model, xd)  # public API: y = g(x) copies x in, replays, returns a copy of the output
         with torch.no_grad():
             for _ in range(warmup):
-                out = model(xd)
+                out = fwd(xd)
             barrier()
             sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
             l0 = ops.LAUNCHES
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(n_steps):
-                out = model(xd)
+                out = fwd(xd)
             e1.record()
             barrier()
             ms = max_over_ranks(e0.elapsed_time(e1)) / n_steps
@@ -553,6 +564,9 @@ def main() -> None:
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["desc"], "per_gpu_batch": B, "global_batch": B * world,
                        "parallelism": f"dp{world} (batch-sharded, no collective)", "weights": "random-init, seed 0",
+                       "launch": ("one CUDA-graph replay per forward (graphs.GraphedForward; the e2e legs and the "
+                                  "per-launch profile use the launch plan / single calls)") if use_graph else
+                                 "launch plan: one b200enc_run_ops call per forward (plans.py)",
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)" if B >= 64 else
                              "per-step activations may fit the 126 MB L2 at this batch",
                        "numa": numa},

@@ -31,6 +31,14 @@ constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_THREADS = 384;  // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1, 2: softmax
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128B-swizzled
+#ifndef ATT_V6_MAX3
+#define ATT_V6_MAX3 1  // row maximum: 1 = four chains of FMNMX3, 0 = two chains of FMNMX (first form)
+#endif
+__device__ __forceinline__ float v6_fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 #ifndef ATT_V6_PLAIN
 #define ATT_V6_PLAIN 0  // 1: the softmax warps spin on their barriers without the bound (A/B of what the bound costs)
 #endif
@@ -182,6 +190,9 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
                                               const float* bias_row = nullptr, int n_cols = 0) {
   uint32_t v[4][32];
   float mx0 = -INFINITY, mx1 = -INFINITY;
+#if ATT_V6_MAX3
+  float mx2 = -INFINITY, mx3 = -INFINITY;
+#endif
   const float c_in = c;
   auto prep_max = [&](int ch) {  // bias, mask and running maximum of one 32-column chunk (ch is a literal after unrolling)
     if (kBias) {
@@ -197,11 +208,24 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
       for (int i = 0; i < 32; ++i)
         if (ch * 32 + i >= lim) v[ch][i] = 0xff800000u;
     }
+#if ATT_V6_MAX3
+    // four chains of three-input maxima (FMNMX3: two scores per instruction): the two-chain form is bound by the
+    // latency of 64 dependent FMNMX (~450 clocks per block in the trace — on the critical path now that the softmax
+    // warps no longer wait for the tensor core)
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      mx0 = v6_fmax3(mx0, __uint_as_float(v[ch][i]), __uint_as_float(v[ch][i + 1]));
+      mx1 = v6_fmax3(mx1, __uint_as_float(v[ch][i + 2]), __uint_as_float(v[ch][i + 3]));
+      mx2 = v6_fmax3(mx2, __uint_as_float(v[ch][i + 4]), __uint_as_float(v[ch][i + 5]));
+      mx3 = v6_fmax3(mx3, __uint_as_float(v[ch][i + 6]), __uint_as_float(v[ch][i + 7]));
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       mx0 = fmaxf(mx0, __uint_as_float(v[ch][i]));
       mx1 = fmaxf(mx1, __uint_as_float(v[ch][i + 1]));
     }
+#endif
   };
   tmem_ld32(tS, v[0]);
   if (1 < n_chunks) tmem_ld32(tS + 32, v[1]);
@@ -218,7 +242,11 @@ __device__ __forceinline__ void softmax_block(uint32_t tS, uint32_t tP, const So
   if (2 < n_chunks) prep_max(2);
   if (3 < n_chunks) prep_max(3);
   if (kBias) c = 1.0f;
+#if ATT_V6_MAX3
+  const float m_new = v6_fmax3(m, fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+#else
   const float m_new = fmaxf(m, fmaxf(mx0, mx1));
+#endif
   // lazy rescale: only when some row of this warp gained more than ATT_RESCALE_LOG2 of head-room (always true for
   // the first block with a visible key, where m = -inf)
   rescale = __any_sync(0xffffffffu, (m_new - m) * c > ATT_RESCALE_LOG2);
