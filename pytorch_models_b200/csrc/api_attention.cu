@@ -2,13 +2,10 @@
 #include <cstdlib>
 
 #include "../../include/b200enc.h"
-#ifdef ATT_V6
-#include "attention_v6.cuh"
-#else
 #include "attention.cuh"
 #include "attention_short.cuh"
 #include "attention_short_split.cuh"
-#endif
+#include "attention_v6.cuh"
 #include "host_util.h"
 
 using namespace b200;
@@ -38,22 +35,53 @@ int launch_pdl(Kern kern, int grid, int threads, int smem, cudaStream_t s, const
   return 0;
 }
 
-int launch_attention(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
-                     const AttnParams& p, cudaStream_t s) {
+// The streaming kernel: attention_v6.cuh (separate P columns, scores issued a block ahead); the previous kernel
+// (attention.cuh) stays reachable with B200ENC_ATTN_V5=1 for same-box A/B runs and its self-tests.
+template <typename P>
+void fill_params(P& p, int B, int H, int Lq, int Lkv, float scale, void* out, long long out_batch_stride, int ldo, int flags,
+                 const float* bias, long long bias_b_stride, long long bias_h_stride, long long bias_row_stride,
+                 long long* trace) {
+  p.B = B;
+  p.H = H;
+  p.Lq = Lq;
+  p.Lkv = Lkv;
+  p.n_qp = (Lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
+  p.n_items = B * H * p.n_qp;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out_batch_stride = out_batch_stride;
+  p.ldo = ldo;
+  p.causal = (flags & B200ENC_ATTN_CAUSAL) ? 1 : 0;
+  p.bias = bias;
+  p.bias_b_stride = bias_b_stride;
+  p.bias_h_stride = bias_h_stride;
+  p.bias_row_stride = bias_row_stride;
+  p.abort_word = abort_word();
+  p.debug_fault = (flags >> 16) & 1;  // selftest only (B200ENC_ATTN_DEBUG_FAULT)
+  p.trace = trace;
+}
+
+template <typename KernT, typename KernF, typename P>
+int launch_streaming(KernT kern_bias, KernF kern_plain, int threads, int smem, const CUtensorMap& tq, const CUtensorMap& tk,
+                     const CUtensorMap& tv, const CUtensorMap& to, const P& p, cudaStream_t s) {
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (p.bias != nullptr) {
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<true>), ATT_SMEM_BYTES)) return rc;
-    return launch_pdl(attention_kernel<true>, grid, ATT_THREADS, ATT_SMEM_BYTES, s, tq, tk, tv, to, p);
-  } else {
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel<false>), ATT_SMEM_BYTES)) return rc;
-    return launch_pdl(attention_kernel<false>, grid, ATT_THREADS, ATT_SMEM_BYTES, s, tq, tk, tv, to, p);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern_bias), smem)) return rc;
+    return launch_pdl(kern_bias, grid, threads, smem, s, tq, tk, tv, to, p);
   }
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern_plain), smem)) return rc;
+  return launch_pdl(kern_plain, grid, threads, smem, s, tq, tk, tv, to, p);
+}
+
+bool use_v5() {
+  static const bool v = [] {
+    const char* e = getenv("B200ENC_ATTN_V5");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
 }
 }  // namespace
 
-#ifndef ATT_V6
 // Lkv <= 256, no mask: the single-pass kernel of attention_short.cuh. TMEM layout (see its header): private columns
 // for S and O where 512 columns allow it, otherwise O_t over the upper columns of S_t.
 static int attention_short_impl(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
@@ -113,7 +141,6 @@ static int attention_short_impl(const void* q, long long q_batch_stride, int ldq
   if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), ATS_SMEM_BYTES))) return rc;
   return launch_pdl(kern, grid, ATT_THREADS, ATS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, to, p);
 }
-#endif
 
 static int attention_impl(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,
                           long long kv_batch_stride, int ldkv, void* out, long long out_batch_stride, int ldo, int B,
@@ -130,11 +157,9 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
                  "b200enc_attention: output rows must be 16-byte aligned");
   CUtensorMap tq, tk, tv, to;
   int rc;
-#ifndef ATT_V6
   if (Lkv <= ATS_MAX_KV && bias == nullptr && !(flags & (B200ENC_ATTN_CAUSAL | B200ENC_ATTN_GENERAL)))
     return attention_short_impl(q, q_batch_stride, ldq, k, v, kv_batch_stride, ldkv, out, out_batch_stride, ldo, B, H, Lq,
                                 Lkv, scale, flags, stream);
-#endif
   const long long qbs = B > 1 ? q_batch_stride : (long long)Lq * ldq;
   const long long kbs = B > 1 ? kv_batch_stride : (long long)Lkv * ldkv;
   if ((rc = make_tmap_bf16(&tq, q, uint64_t(H) * ATT_HD, Lq, B, ldq, qbs, ATT_HD, ATT_BQ, 128))) return rc;
@@ -143,31 +168,23 @@ static int attention_impl(const void* q, long long q_batch_stride, int ldq, cons
   // output: one TMA store of 32 rows x 64 columns per softmax warp; rows >= Lq of a batch are clipped by the map
   const long long obs = B > 1 ? out_batch_stride : (long long)Lq * ldo;
   if ((rc = make_tmap_bf16(&to, out, uint64_t(H) * ATT_HD, Lq, B, ldo, obs, ATT_HD, 32, 128))) return rc;
-  AttnParams p;
-  p.B = B;
-  p.H = H;
-  p.Lq = Lq;
-  p.Lkv = Lkv;
-  p.n_qp = (Lq + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
-  p.n_items = B * H * p.n_qp;
-  p.scale_log2e = scale * 1.4426950408889634f;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.out_batch_stride = out_batch_stride;
-  p.ldo = ldo;
-  p.causal = (flags & B200ENC_ATTN_CAUSAL) ? 1 : 0;
-  p.bias = bias;
-  p.bias_b_stride = bias_b_stride;
-  p.bias_h_stride = bias_h_stride;
-  p.bias_row_stride = bias_row_stride;
-  p.abort_word = abort_word();
-  p.debug_fault = (flags >> 16) & 1;  // selftest only (B200ENC_ATTN_DEBUG_FAULT)
 #ifdef ATT_TRACE
-  p.trace = g_attention_trace;
+  long long* const trace = g_attention_trace;
 #else
-  p.trace = nullptr;
+  long long* const trace = nullptr;
 #endif
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return launch_attention(tq, tk, tv, to, p, s);
+  if (use_v5()) {
+    AttnParams p;
+    fill_params(p, B, H, Lq, Lkv, scale, out, out_batch_stride, ldo, flags, bias, bias_b_stride, bias_h_stride,
+                bias_row_stride, trace);
+    return launch_streaming(attention_kernel<true>, attention_kernel<false>, ATT_THREADS, ATT_SMEM_BYTES, tq, tk, tv, to, p, s);
+  }
+  v6::AttnParams p;
+  fill_params(p, B, H, Lq, Lkv, scale, out, out_batch_stride, ldo, flags, bias, bias_b_stride, bias_h_stride,
+              bias_row_stride, trace);
+  return launch_streaming(v6::attention_kernel<true>, v6::attention_kernel<false>, v6::ATT_THREADS, v6::ATT_SMEM_BYTES, tq,
+                          tk, tv, to, p, s);
 }
 
 extern "C" int b200enc_attention(const void* q, long long q_batch_stride, int ldq, const void* k, const void* v,

@@ -21,10 +21,12 @@
 // Q/K/V are read straight out of the fused QKV activation [rows, 3d] through strided 3-D tensor maps (no head
 // transpose is materialised); the output is written head-interleaved as [rows, d] for out_proj.
 #pragma once
-// EXPERIMENTAL (round 2): not included by the library build unless -DATT_V6; see DESIGN.md section 3.2 for the measurements.
+// Round 2, second session: this is the shipped streaming kernel (api_attention.cu); attention.cuh is the previous one,
+// kept behind B200ENC_ATTN_V5=1 for same-box A/B runs. See DESIGN.md section 3.2 for the measurements.
 #include "ptx.cuh"
 
 namespace b200 {
+namespace v6 {
 
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
@@ -39,31 +41,26 @@ __device__ __forceinline__ float v6_fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-#ifndef ATT_V6_PLAIN
-#define ATT_V6_PLAIN 0  // 1: the softmax warps spin on their barriers without the bound (A/B of what the bound costs)
-#endif
-#if ATT_V6_PLAIN
+// Every role spins on its barriers with the tightest loop (a bounded loop in the softmax warps costs 3-5 % here, same
+// box A/B); the watchdog warp bounds them from outside, exactly as in attention.cuh.
 #define V6_WAIT(b, par, ctx) mbar_wait_plain(b, par)
-#else
-#define V6_WAIT(b, par, ctx) mbar_wait(b, par, ctx)
-#endif
 #ifndef ATT_V6_LEAN
 #define ATT_V6_LEAN 1  // MMA issuer: 1 = hoisted waits + three elected regions per block (see the issuer), 0 = first form
 #endif
-#ifndef ATT_MMA_ORDER
-#define ATT_MMA_ORDER 0  // 0: PV0 PV1 QK0 QK1 per block (shipped); 1: PV0 QK0 PV1 QK1 (measured slower at L=197)
+#ifndef V6_MMA_ORDER
+#define V6_MMA_ORDER 0  // 0: PV0 PV1 QK0 QK1 per block (shipped); 1: PV0 QK0 PV1 QK1 (measured slower at L=197)
 #endif
-#ifndef ATT_KV_STAGES
-#define ATT_KV_STAGES 4  // blocks n .. n+2 are live in the issuer's stream (P.V of n, Q.K of n+2) + one being fetched
+#ifndef V6_KV_STAGES
+#define V6_KV_STAGES 4  // blocks n .. n+2 are live in the issuer's stream (P.V of n, Q.K of n+2) + one being fetched
 #endif
 constexpr int ATT_TM_TILE = 256;  // TMEM columns per query tile
 constexpr int ATT_TM_P = 128;     //   P (bf16 pairs) at [128, 192)
 constexpr int ATT_TM_O = 192;     //   O accumulator at [192, 256)
 constexpr int ATT_SMEM_Q = 0;                                   // 2 buffers x 2 tiles
-constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // ATT_KV_STAGES tiles
-constexpr int ATT_SMEM_V = ATT_SMEM_K + ATT_KV_STAGES * ATT_TILE_BYTES;
+constexpr int ATT_SMEM_K = 4 * ATT_TILE_BYTES;                  // V6_KV_STAGES tiles
+constexpr int ATT_SMEM_V = ATT_SMEM_K + V6_KV_STAGES * ATT_TILE_BYTES;
 constexpr int ATT_STG_BYTES = 32 * 128;                          // one softmax warp's output rows: 32 x 64 bf16
-constexpr int ATT_SMEM_STG = ATT_SMEM_V + ATT_KV_STAGES * ATT_TILE_BYTES;  // 8 warps, 1024-aligned
+constexpr int ATT_SMEM_STG = ATT_SMEM_V + V6_KV_STAGES * ATT_TILE_BYTES;  // 8 warps, 1024-aligned
 constexpr int ATT_SMEM_BAR = ATT_SMEM_STG + 8 * ATT_STG_BYTES;
 constexpr int ATT_SOFTMAX_REGS = 208;  // setmaxnreg: the increase blocks until the control warpgroup has released enough
 constexpr int ATT_CONTROL_REGS = 88;   //   (the kernel starts with 168 x 384 = 64512 registers: 4 x 32 x 88 + 8 x 32 x 208 uses exactly that)
@@ -85,7 +82,7 @@ struct AttnParams {
   long long bias_b_stride, bias_h_stride, bias_row_stride;
   long long* trace;   // debug only: (event, clock) records of CTA 0 (nullptr in production)
   unsigned int* abort_word;  // raised by a bounded barrier wait that ran out (ptx.cuh: mbar_wait); may be nullptr
-  int debug_fault;           // unused here (attention.cuh: watchdog self-test)
+  int debug_fault;           // selftest only: 1 = CTA 0 drops one S_FULL commit (a protocol slip) to exercise the watchdog
 };
 
 #ifdef ATT_TRACE
@@ -170,7 +167,7 @@ struct SoftmaxSync {
 // during which the pipe idles. A purely advisory hand-over keeps them in anti-phase instead: a warp entering its
 // exponential phase first waits (bounded, no correctness role) while the other warp's "busy" word is set.
 #ifndef ATT_SKEW_CLKS
-#define ATT_SKEW_CLKS 0
+#define ATT_SKEW_CLKS 1500  // one-time phase offset of tile 1's softmax warps (same box: -1.5 % at L = 1370 / 1500)
 #endif
 #ifndef ATT_TURN_SPINS
 #define ATT_TURN_SPINS 0  // x ~30 clocks per probe: gives up after ~3000 clocks (longer than any exponential phase)
@@ -314,12 +311,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // barrier slots: q_full[2], q_empty[2], s_full[2], s_empty[2], p_full[2], o_full[2], kv_full[stages], kv_empty[stages]
   auto bar = [&](int i) { return bars + 8u * i; };
   constexpr int Q_FULL = 0, Q_EMPTY = 2, S_FULL = 4, S_EMPTY = 6, P_FULL = 8, O_FULL = 10, KV_FULL = 12,
-                KV_EMPTY = 12 + ATT_KV_STAGES;
-  static_assert(8 * (12 + 2 * ATT_KV_STAGES) + 4 <= 224, "barrier block overflows into the hand-over words");
+                KV_EMPTY = 12 + V6_KV_STAGES, DONE = 12 + 2 * V6_KV_STAGES;
+  constexpr int kProtocolBarriers = DONE;  // every barrier below DONE takes part in the data-flow protocol
+  static_assert(kProtocolBarriers <= 32, "the watchdog flips one protocol barrier per lane");
+  static_assert(8 * (DONE + 1) + 8 <= 224, "barrier block overflows into the hand-over words");
   const uint32_t turns = sbase + ATT_SMEM_BAR + 224;  // 8 words: busy[tile][lane quarter]
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * (12 + 2 * ATT_KV_STAGES));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + ATT_SMEM_BAR + 8 * (DONE + 1));
+  const uint32_t progress_addr = sbase + ATT_SMEM_BAR + 8 * (DONE + 1) + 4;  // blocks issued by the MMA warp (watchdog input)
   unsigned int* const abw = p.abort_word;
-  WaitCtx wctx = make_wait_ctx(abw);
+  WaitCtx wctx = make_wait_ctx(abw);  // only handed through to softmax_block; every wait is plain (see V6_WAIT)
 
 #if ATT_ROLES_HI
   // Role index, not the hardware warp id: the SM sub-partition's arbiter serves the HIGHEST warp id first (measured,
@@ -350,10 +350,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(bar(P_FULL + i), 4);
       mbar_init(bar(O_FULL + i), 1);
     }
-    for (int s = 0; s < ATT_KV_STAGES; ++s) {
+    for (int s = 0; s < V6_KV_STAGES; ++s) {
       mbar_init(bar(KV_FULL + s), 1);
       mbar_init(bar(KV_EMPTY + s), 1);
     }
+    mbar_init(bar(DONE), 10);  // producer, MMA issuer and the eight softmax warps arrive when they run out of work
+    sts_volatile(progress_addr, 0u);
     for (int i = 0; i < 8; ++i) sts_volatile(turns + 4u * i, 0u);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
@@ -369,6 +371,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // (ptx.cuh: programmatic dependent launch; nothing above touched global memory)
+  griddep_wait();
   const int n_kvb = (p.Lkv + ATT_BKV - 1) / ATT_BKV;
   // K/V blocks a query tile has to visit: all of them, or with a causal mask only those up to its last row's diagonal
   auto tile_blocks = [&](int item, int t) {
@@ -390,7 +394,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int b = bh / p.H;
       const bool two = qp * 256 + ATT_BQ < p.Lq;  // second query tile has at least one valid row
       const uint32_t qb = it & 1u;
-      mbar_wait(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u, wctx);
+      mbar_wait_plain(bar(Q_EMPTY + qb), ((it >> 1) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(bar(Q_FULL + qb), (two ? 2 : 1) * ATT_TILE_BYTES);
         const uint32_t sq = sbase + ATT_SMEM_Q + qb * 2 * ATT_TILE_BYTES;
@@ -400,19 +404,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       const int nb = item_blocks(item);
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(bar(KV_EMPTY + stage), phase ^ 1u, wctx);
+        mbar_wait_plain(bar(KV_EMPTY + stage), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(bar(KV_FULL + stage), 2 * ATT_TILE_BYTES);
           tma_load_3d(&tmK, bar(KV_FULL + stage), sbase + ATT_SMEM_K + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
           tma_load_3d(&tmV, bar(KV_FULL + stage), sbase + ATT_SMEM_V + stage * ATT_TILE_BYTES, h * ATT_HD, j * ATT_BKV, b);
         }
         __syncwarp();
-        if (++stage == ATT_KV_STAGES) {
+        if (++stage == V6_KV_STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
+    if (lane == 0) mbar_arrive(bar(DONE));
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
     {
@@ -421,6 +426,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // S buffers that the softmax warps released when they pulled block n+1 into registers. Per tile the order is
       // QK(n+1) PV(n) QK(n+2) PV(n+1) ..., each waiting on an event of that tile's softmax warps in the order in which
       // they occur (S_EMPTY(n+1) before P_FULL(n+1)), so the stream never waits on something that needs a later MMA.
+      uint32_t blocks_done = 0;
       uint32_t nqk[2] = {0, 0};  // score MMAs issued so far per tile (S_EMPTY parity)
       uint32_t npv[2] = {0, 0};  // P.V MMAs issued so far per tile (P_FULL parity)
       const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
@@ -437,25 +443,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto n_mma_of = [&](int j) { return (min(ATT_BKV, p.Lkv - j * ATT_BKV) + 15) & ~15; };
       auto issue_qk = [&](const Blk& bl, int t) {
         if (nqk[t] > 0) {  // the softmax warps of this tile hold the previous scores in registers
-          mbar_wait(bar(S_EMPTY + t), (nqk[t] - 1) & 1u, wctx);
+          mbar_wait_plain(bar(S_EMPTY + t), (nqk[t] - 1) & 1u);
           tc_fence_after();
         }
         const uint32_t sq = sbase + ATT_SMEM_Q + (bl.it & 1u) * 2 * ATT_TILE_BYTES + t * ATT_TILE_BYTES;
         const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
         const uint64_t dk = make_smem_desc_sw128(sbase + ATT_SMEM_K + bl.stage * ATT_TILE_BYTES, 16, 1024);
         const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, n_mma_of(bl.j), 0, 0);
+        const bool drop_commit = p.debug_fault == 1 && blockIdx.x == 0 && bl.it == 0 && bl.j == 0 && t == 0;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_HD / 16; ++k)
             umma_ss(tmem_base + t * ATT_TM_TILE, dq + 2u * k, dk + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(bar(S_FULL + t));
+          if (!drop_commit) umma_commit(bar(S_FULL + t));
         }
         __syncwarp();
         ++nqk[t];
         if (lane == 0) ATT_EV(100 + t);
       };
       auto issue_pv = [&](const Blk& bl, int t) {
-        mbar_wait(bar(P_FULL + t), npv[t] & 1u, wctx);
+        mbar_wait_plain(bar(P_FULL + t), npv[t] & 1u);
         if (lane == 0) ATT_EV(110 + t);
         tc_fence_after();
         // descriptors are built outside the elected branch (uniform registers); per K step only immediates change:
@@ -478,8 +485,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // wait for the operands of a block (and, for the first block of an item, its Q tiles), then issue its scores
       auto start_block = [&](const Blk& bl, int t_first, int t_last) {
         if (t_first == 0) {
-          if (bl.j == 0) mbar_wait(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u, wctx);
-          mbar_wait(bar(KV_FULL + bl.stage), bl.phase, wctx);
+          if (bl.j == 0) mbar_wait_plain(bar(Q_FULL + (bl.it & 1u)), (bl.it >> 1) & 1u);
+          mbar_wait_plain(bar(KV_FULL + bl.stage), bl.phase);
           if (lane == 0) ATT_EV(130);
           tc_fence_after();
         }
@@ -492,7 +499,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       };
       auto advance = [&](Blk bl) {
-        if (++bl.stage == ATT_KV_STAGES) {
+        if (++bl.stage == V6_KV_STAGES) {
           bl.stage = 0;
           bl.phase ^= 1u;
         }
@@ -578,6 +585,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (lane == 0) ATT_EV(100);
           if (qk0) ++nqk[0];
           if (qk1) ++nqk[1];
+          if (lane == 0) sts_volatile(progress_addr, ++blocks_done);  // the watchdog's sign of life
           if (!have1) break;
           cur = nx1;
           nx1 = nx2;
@@ -598,7 +606,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             nx2 = advance(nx1);
             have2 = nx2.item < p.n_items;
           }
-#if ATT_MMA_ORDER == 0
+#if V6_MMA_ORDER == 0
           // P.V of both tiles first: a tile that has published its probabilities (in particular its last ones: the
           // item's epilogue waits for this P.V) is never queued behind the other tile's S_EMPTY, which at an item
           // boundary only comes after that tile's epilogue. The scores of block n+2 are not needed before the
@@ -614,6 +622,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #endif
           if (elect_one()) umma_commit(bar(KV_EMPTY + cur.stage));  // free once everything issued so far completes
           __syncwarp();
+          if (lane == 0) sts_volatile(progress_addr, ++blocks_done);
           if (!have1) break;
           cur = nx1;
           nx1 = nx2;
@@ -621,6 +630,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
 #endif
+      if (lane == 0) mbar_arrive(bar(DONE));
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ watchdog (attention.cuh: the working warps spin
+    // unbounded; this warp sleeps on DONE and, if the issuer's block counter stops moving for B200_WAIT_LIMIT_NS,
+    // raises the library's abort word and keeps flipping every protocol barrier until all roles have drained)
+    if (abw != nullptr) {
+      uint32_t last = 0xFFFFFFFFu;
+      uint64_t t_last = 0;
+      bool raised = false;
+      while (!mbar_try_wait_hint(bar(DONE), 0u, 20000u)) {
+        const uint64_t now = global_timer_ns();
+        const uint32_t pr = lds_volatile(progress_addr);
+        if (pr != last || t_last == 0) {
+          last = pr;
+          t_last = now;
+        } else if (now - t_last > B200_WAIT_LIMIT_NS) {
+          if (!raised && lane == 0) {
+            *reinterpret_cast<volatile unsigned int*>(abw) = 0xB200DEADu;
+            __threadfence_system();
+          }
+          raised = true;
+          if (lane < kProtocolBarriers) {
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) mbar_arrive(bar(lane));
+          }
+          __nanosleep(2000);
+        }
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / output warpgroups
@@ -758,6 +796,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DONE));
   }
 
   tc_fence_before();
@@ -769,4 +808,5 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+}  // namespace v6
 }  // namespace b200
