@@ -147,6 +147,33 @@ def test_encoder_and_decoder_replay():
     _check_replay(post, lambda r: (torch.randn(3, 40, 128, device="cuda", dtype=torch.bfloat16),))
 
 
+def test_whisper_encoder_and_bert_replay(golden):
+    g = golden("whisper")
+    m = build_model(g).cuda()
+    shape = g.input.shape
+
+    def mel(r):
+        torch.manual_seed(50 + r)
+        return (torch.randn(*shape, device="cuda"),)
+
+    _check_replay(m, mel)
+    _check_replay(m.bfloat16(), lambda r: (mel(r)[0].bfloat16(),))
+    g = golden("bert")
+    b = build_model(g).cuda()
+    ids0 = torch.from_numpy(np.array(g.input)).cuda()
+    vocab = int(ids0.max().item()) + 1
+
+    def ids(r):
+        torch.manual_seed(70 + r)
+        return (torch.randint(0, vocab, tuple(ids0.shape), device="cuda"),)
+
+    _check_replay(b, ids)
+    with torch.no_grad():
+        got = b(ids0).float().cpu().numpy()      # replay on the fixture's ids
+    want = g.out["tokens"]
+    assert float(np.abs(got - want).max()) <= 0.125 * max(1.0, float(np.abs(want).max()) / 4.0)
+
+
 def test_profiling_bypasses_plans(golden):
     m = build_model(golden("vit_cls")).cuda().bfloat16()
     x = torch.randn(2, *golden("vit_cls").input.shape[1:], device="cuda", dtype=torch.bfloat16)
