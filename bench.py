@@ -77,11 +77,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int) -> None:
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []  # (arrival time, csv line)
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -90,9 +90,12 @@ class ClockSampler:
 
     def _pump(self) -> None:
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Median SM clock / reasons over the samples that arrived inside [t0, t1] (host times bracketing the timed
+        region). The sampler is started before the warm-up steps; if the timed region is shorter than the sampling
+        interval and holds no sample, the samples of warm-up + timed region are used and the line says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -102,7 +105,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        window = "timed region"
+        lines = [ln for ts, ln in self.lines if t0 is None or t0 <= ts <= (t1 if t1 is not None else ts)]
+        if not lines:
+            lines = [ln for _, ln in self.lines]
+            window = "warm-up + timed region (the timed region is shorter than the sampling interval)"
+        for line in lines:
             f = [t.strip() for t in line.split(",")]
             if len(f) < 7:
                 continue
@@ -116,7 +124,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks() -> dict:
@@ -243,6 +251,10 @@ def main() -> None:
                     help="device-rate loop: replay the forward as one CUDA graph (graphs.GraphedForward). auto = when the "
                          "per-GPU batch is at most 256 images (the strong-scaled shards), where 64 stream launches "
                          "cost the GPU ~7 %% more than one graph launch")
+    ap.add_argument("--prewarm", type=float, default=1.0,
+                    help="seconds of untimed forwards before the W warm-up steps of the device-rate leg: short strong-"
+                         "scaled runs (20 steps x 4.5 ms at 128 images per GPU) would otherwise be timed at the boost "
+                         "clocks of a cold GPU while the legs after them run power-capped")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -305,19 +317,26 @@ def main() -> None:
 
             fwd = GraphedForward(model, xd)  # public API: y = g(x) copies x in, replays, returns a copy of the output
         with torch.no_grad():
+            t_pre = time.perf_counter()
+            while sample_clocks and time.perf_counter() - t_pre < args.prewarm:  # reach the sustained clock regime
+                for _ in range(4):
+                    fwd(xd)
+                torch.cuda.synchronize()
+            sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
             for _ in range(warmup):
                 out = fwd(xd)
             barrier()
-            sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
             l0 = ops.LAUNCHES
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_host0 = time.perf_counter()
             e0.record()
             for _ in range(n_steps):
                 out = fwd(xd)
             e1.record()
             barrier()
+            t_host1 = time.perf_counter()
             ms = max_over_ranks(e0.elapsed_time(e1)) / n_steps
-            return ms, ops.LAUNCHES - l0, (sampler.stop() if sampler else None), out, xd
+            return ms, ops.LAUNCHES - l0, (sampler.stop(t_host0, t_host1) if sampler else None), out, xd
 
     # ---- device-resident throughput ("value")
     if os.environ.get("B200_PROFILE_STEP"):
@@ -569,6 +588,7 @@ def main() -> None:
                                  "launch plan: one b200enc_run_ops call per forward (plans.py)",
                        "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)" if B >= 64 else
                              "per-step activations may fit the 126 MB L2 at this batch",
+                       "prewarm": f"{args.prewarm:g} s of untimed forwards before the {warmup} warm-up steps (sustained clocks)",
                        "numa": numa},
             "tokens_per_s": value * cfg["L"],
             "model_tflops": value * fl / 1e12, "model_frac_of_burst_peak": value * fl / 1e12 / world / peaks["burst"],
