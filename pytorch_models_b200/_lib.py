@@ -10,7 +10,9 @@ import os
 from ctypes import c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200enc.so")
+# B200ENC_LIB: load another build of the same library instead (same-box A/B of compile-time variants:
+# `make -C pytorch_models_b200/csrc variant NAME=ab_x DEFS=-D...` -> pytorch_models_b200/ab_x/libb200enc.so)
+LIB_PATH = os.environ.get("B200ENC_LIB") or os.path.join(_HERE, "libb200enc.so")
 
 LINEAR_GELU = 1
 LINEAR_GELU_TANH = 2
