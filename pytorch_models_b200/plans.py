@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
+import weakref
 from collections import OrderedDict
 from ctypes import c_float, c_int, c_longlong, c_void_p
 
@@ -31,6 +32,9 @@ ENABLED = os.environ.get("B200ENC_PLANS", "1") != "0"
 MAX_PLANS_PER_MODULE = 4
 STATS = {"recorded": 0, "replayed": 0, "unplannable": 0}
 _EPOCH = 0
+# module -> OrderedDict[key, LaunchPlan | None]. Kept OUTSIDE the module's __dict__: plans hold ctypes arrays and a lock,
+# which copy.deepcopy / pickle (EMA copies, torch.save(model)) must never meet; a copied module simply records its own.
+_PLANS: "weakref.WeakKeyDictionary[nn.Module, OrderedDict]" = weakref.WeakKeyDictionary()
 _LINEAR_PTR_FIELDS = ("x", "w", "bias", "colsum", "rowstats", "residual", "out", "stats_out", "acc_scale")
 _LINEAR_PTR_TYPE = ctypes.POINTER(_lib.LinearArgs)
 
@@ -74,14 +78,15 @@ class _Signature:
                     if isinstance(v, Tensor) and id(v) not in seen:
                         seen.add(id(v))
                         self.tensors.append(v)
-        self.root = module
+        self.root = weakref.ref(module)  # weak: the plan cache is keyed by the module and must not keep it alive
         self.state = self._state()
 
     def _state(self) -> list:
         return [(t.data_ptr(), _version(t)) for t in self.tensors]
 
     def valid(self) -> bool:
-        if self.root.training != self.training:
+        root = self.root()
+        if root is None or root.training != self.training:
             return False
         for d, n in self.dicts:
             if len(d) != n:
@@ -209,9 +214,9 @@ def run(module: nn.Module, inputs: tuple[Tensor, ...], fn, extra_key: tuple = ()
     dev = inputs[0].device
     stream = torch.cuda.current_stream(dev).cuda_stream
     key = (tuple((tuple(t.shape), t.dtype) for t in inputs), dev, stream, extra_key)
-    cache: OrderedDict = module.__dict__.get("_b200_plans")
+    cache = _PLANS.get(module)
     if cache is None:
-        cache = module.__dict__["_b200_plans"] = OrderedDict()
+        cache = _PLANS[module] = OrderedDict()
     plan = cache.get(key, False)
     if plan is None:  # recorded before and found unplannable
         return fn(*inputs)
@@ -252,4 +257,9 @@ def run(module: nn.Module, inputs: tuple[Tensor, ...], fn, extra_key: tuple = ()
 
 def clear(module: nn.Module) -> None:
     """Forget the plans of ``module`` (and free the workspaces they hold)."""
-    module.__dict__.pop("_b200_plans", None)
+    _PLANS.pop(module, None)
+
+
+def plans_of(module: nn.Module) -> dict:
+    """The recorded plans of ``module`` by key (None = a forward that turned out not to be plannable); for tests."""
+    return dict(_PLANS.get(module, {}))

@@ -75,7 +75,7 @@ def test_replay_is_one_library_call_and_counts_launches(golden):
         n1 = ops.LAUNCHES
         m(x)
         assert ops.LAUNCHES - n1 == per_forward     # the replay launches (and counts) the same kernels
-    plan = next(iter(m.__dict__["_b200_plans"].values()))
+    plan = next(iter(plans.plans_of(m).values()))
     assert plan is not None and plan.n == per_forward
 
 
@@ -116,7 +116,7 @@ def test_shapes_and_streams_get_their_own_plans(golden):
             y_again = m(x)
         side.synchronize()
         assert torch.equal(y, y_again) and torch.equal(y, _per_launch(lambda: m(x)))
-    assert len(m.__dict__["_b200_plans"]) == 3
+    assert len(plans.plans_of(m)) == 3
 
 
 def test_outputs_of_successive_replays_do_not_alias(golden):
@@ -172,6 +172,34 @@ def test_whisper_encoder_and_bert_replay(golden):
         got = b(ids0).float().cpu().numpy()      # replay on the fixture's ids
     want = g.out["tokens"]
     assert float(np.abs(got - want).max()) <= 0.125 * max(1.0, float(np.abs(want).max()) / 4.0)
+
+
+def test_modules_with_plans_can_be_copied_pickled_and_collected(golden):
+    """Plans live outside the module: deepcopy (EMA copies) and pickling (torch.save(model)) keep working after a
+    forward, the copy records its own plan, and a dropped module releases its plan (and the workspaces it owns)."""
+    import copy
+    import gc
+    import io
+    import weakref
+
+    g = golden("vit_cls")
+    m = build_model(g).cuda().bfloat16()
+    x = torch.randn(2, *g.input.shape[1:], device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        y = m(x)
+        assert torch.equal(m(x), y) and len(plans.plans_of(m)) == 1
+        twin = copy.deepcopy(m)
+        assert len(plans.plans_of(twin)) == 0 and torch.equal(twin(x), y) and torch.equal(twin(x), y)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        loaded = torch.load(buf, weights_only=False)
+        assert torch.equal(loaded(x), y)
+    ref = weakref.ref(m)
+    plan_ref = weakref.ref(next(iter(plans.plans_of(m).values())))
+    del m
+    gc.collect()
+    assert ref() is None and plan_ref() is None
 
 
 def test_profiling_bypasses_plans(golden):

@@ -97,6 +97,24 @@ def test_cpu_tensors_still_raise_with_plans_enabled():
         enc(torch.zeros(1, 4, 64))
 
 
+def test_plan_cache_lives_outside_the_module():
+    """deepcopy / pickle of a module must never meet a plan (ctypes arrays, a lock): the cache is a weak map keyed by
+    the module, and a signature does not keep its module alive."""
+    import copy
+    import gc
+    import weakref
+
+    m = pm.ViT(1, 64, 1, 16, img_size=32).eval()
+    plans._PLANS[m] = {"k": object()}
+    sig = plans._Signature(m)
+    twin = copy.deepcopy(m)
+    assert plans.plans_of(twin) == {} and "_b200_plans" not in m.__dict__
+    ref = weakref.ref(m)
+    del m
+    gc.collect()
+    assert ref() is None and not sig.valid()
+
+
 def test_plans_module_never_imports_the_oracle():
     src = open(os.path.join(ROOT, "pytorch_models_b200", "plans.py")).read()
     assert "oracle" not in src
