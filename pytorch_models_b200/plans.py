@@ -3,8 +3,8 @@
 The reference's forward is a Python loop over modules (``nn.Sequential``, transformer.py:133-149); the drop-in modules
 walk the same loop and make one ctypes call per kernel, ~29 us of interpreter time each — 1.9 ms for the 65 launches
 of a ViT-B/16 forward, against 4.5 ms of GPU time at the 128-image shard of the 8-GPU run. A forward whose body
-consists of `ops.*` calls only is therefore recorded the first time it runs for a given (input shapes, stream,
-weights): every argument of every launch goes into an array of ``b200enc_op``, the tensors the launches touch
+consists of `ops.*` calls only is therefore recorded the SECOND time it runs for a given (input shapes, stream,
+weights) — shapes that occur once (a generation loop over a growing sequence) are not worth a plan: every argument of every launch goes into an array of ``b200enc_op``, the tensors the launches touch
 (workspaces, packed weights) are kept alive by the plan, and the pointers that fall inside the inputs / the output are
 remembered as patch slots. Later forwards allocate a fresh output, patch those slots and enqueue the whole sequence
 with one call. A plan is dropped as soon as a parameter / buffer of the module is replaced, mutated in place
@@ -35,6 +35,7 @@ _EPOCH = 0
 # module -> OrderedDict[key, LaunchPlan | None]. Kept OUTSIDE the module's __dict__: plans hold ctypes arrays and a lock,
 # which copy.deepcopy / pickle (EMA copies, torch.save(model)) must never meet; a copied module simply records its own.
 _PLANS: "weakref.WeakKeyDictionary[nn.Module, OrderedDict]" = weakref.WeakKeyDictionary()
+_SEEN: "weakref.WeakKeyDictionary[nn.Module, OrderedDict]" = weakref.WeakKeyDictionary()  # keys met once, not recorded yet
 _LINEAR_PTR_FIELDS = ("x", "w", "bias", "colsum", "rowstats", "residual", "out", "stats_out", "acc_scale")
 _LINEAR_PTR_TYPE = ctypes.POINTER(_lib.LinearArgs)
 
@@ -220,6 +221,19 @@ def run(module: nn.Module, inputs: tuple[Tensor, ...], fn, extra_key: tuple = ()
     plan = cache.get(key, False)
     if plan is None:  # recorded before and found unplannable
         return fn(*inputs)
+    if plan is False:
+        # first sight of this key: run it plainly and only remember that it occurred. Shapes that never come back
+        # (a generation loop re-running the decoder on a sequence that grows by one token per step, text/generator.py)
+        # would otherwise pay for a signature + a plan + its workspaces on every call and evict the plans that matter.
+        seen = _SEEN.get(module)
+        if seen is None:
+            seen = _SEEN[module] = OrderedDict()
+        if key not in seen:
+            seen[key] = True
+            while len(seen) > 64:
+                seen.popitem(last=False)
+            return fn(*inputs)
+        del seen[key]
     if plan is not False:
         if plan.epoch == _EPOCH and plan.sig.valid():
             cache.move_to_end(key)
@@ -258,6 +272,7 @@ def run(module: nn.Module, inputs: tuple[Tensor, ...], fn, extra_key: tuple = ()
 def clear(module: nn.Module) -> None:
     """Forget the plans of ``module`` (and free the workspaces they hold)."""
     _PLANS.pop(module, None)
+    _SEEN.pop(module, None)
 
 
 def plans_of(module: nn.Module) -> dict:
