@@ -260,3 +260,28 @@ def test_torch_compile_fullgraph_traces_to_one_operator():
     assert a._b200_module_id != b._b200_module_id
     c = copy.deepcopy(a)
     assert c._b200_module_id == a._b200_module_id and pmc.register(c) != a._b200_module_id
+
+
+def test_clock_sampler_windows_its_samples_to_the_timed_region():
+    """bench.ClockSampler: samples are stamped on arrival; stop(t0, t1) reports those inside the timed region, and the
+    warm-up + timed span (saying so) when the region is shorter than the sampling interval."""
+    import bench
+
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+
+    class _Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s.proc = _Done()
+    s.lines = [(1.0, "1900, 1965, 300.0, Not Active, Not Active, Not Active, Not Active"),
+               (2.0, "1200, 1965, 900.0, Not Active, Not Active, Not Active, Active"),
+               (2.1, "1180, 1965, 950.0, Not Active, Not Active, Not Active, Active")]
+    inside = s.stop(1.5, 2.5)
+    assert inside["sm_mhz"] == 1190.0 and inside["samples"] == 2 and inside["reasons"] == ["sw_power_cap"]
+    assert inside["window"] == "timed region" and inside["power_w_max"] == 950.0
+    short = s.stop(3.0, 3.01)
+    assert short["samples"] == 3 and short["window"].startswith("warm-up + timed region")
