@@ -118,3 +118,75 @@ def test_plan_cache_lives_outside_the_module():
 def test_plans_module_never_imports_the_oracle():
     src = open(os.path.join(ROOT, "pytorch_models_b200", "plans.py")).read()
     assert "oracle" not in src
+
+
+def test_run_ops_unpacks_arguments_in_declaration_order():
+    """Every kind reaches its own entry point, and the positional slots land on the right parameters: the argument
+    errors (raised before anything touches the GPU) echo the values that were put into i[]."""
+    lib = _lib.load()
+    failed = ctypes.c_int(-1)
+    ops = (_lib.Op * 1)()
+    for name, kind in _lib.OP_KINDS.items():          # zeroed op: each entry point rejects its own null pointers
+        ops[0] = _lib.Op()
+        ops[0].kind = kind
+        assert lib.b200enc_run_ops(ops, 1, ctypes.byref(failed), None) == -1 and failed.value == 0
+        assert lib.b200enc_last_error().decode().startswith(name + ":"), (name, lib.b200enc_last_error())
+    fake = 0x10000
+    op = _lib.Op()
+    op.kind = _lib.OP_KINDS["b200enc_attention"]
+    for j in range(4):
+        op.p[j] = fake
+    op.i[:12] = (300, 192, 300, 192, 100, 64, 5, 6, 7, 8, 32, 0)   # ..., B, H, Lq, Lkv, head_dim, flags
+    ops[0] = op
+    assert lib.b200enc_run_ops(ops, 1, ctypes.byref(failed), None) == -1
+    assert b"head_dim=32" in lib.b200enc_last_error()
+    op.i[10], op.i[6] = 64, 0
+    ops[0] = op
+    assert lib.b200enc_run_ops(ops, 1, ctypes.byref(failed), None) == -1
+    assert b"B=0 H=6 Lq=7 Lkv=8" in lib.b200enc_last_error()
+    op = _lib.Op()
+    op.kind = _lib.OP_KINDS["b200enc_patch_embed16"]
+    op.linear.x = op.linear.w = op.linear.out = op.linear.residual = fake
+    op.i[0], op.i[1] = 30, 224
+    ops[0] = op
+    assert lib.b200enc_run_ops(ops, 1, ctypes.byref(failed), None) == -1
+    assert b"image 30 x 224" in lib.b200enc_last_error()
+    two = (_lib.Op * 2)()
+    two[0].kind = 99
+    two[1] = op
+    assert lib.b200enc_run_ops(two, 2, ctypes.byref(failed), None) == -1 and failed.value == 0   # stops at the first failure
+
+
+def test_launch_plan_packs_a_recording_and_finds_the_patch_slots():
+    """LaunchPlan from a hand-made recording (CPU tensors stand in for device buffers; nothing is launched): kinds,
+    argument slots, which pointers are patch slots of the input / the output, and what the plan keeps alive."""
+    x = torch.zeros(4, 8, 64, dtype=torch.bfloat16)           # the caller's input
+    out = torch.zeros(4, 8, 64, dtype=torch.bfloat16)         # the forward's fresh output
+    ws = torch.zeros(4 * 8, 192, dtype=torch.bfloat16)        # a workspace the plan must own
+    w = torch.zeros(192, 64, dtype=torch.bfloat16)
+    gamma = torch.ones(64)
+    rec = plans._Recorder()
+    la = _lib.LinearArgs(x.data_ptr(), 0, 64, w.data_ptr(), 64, None, None, None, 0, 0.0, x.data_ptr() + 128, 0, 64,
+                         ws.data_ptr(), 0, 192, None, 1, 32, 192, 64, 0, 0, 0, None)
+    rec.calls.append(("b200enc_linear", (ctypes.byref(la),)))
+    rec.calls.append(("b200enc_layernorm", (ws.data_ptr(), 192, gamma.data_ptr(), gamma.data_ptr(), 1e-6, 32, 64,
+                                            out.data_ptr() + 64, 64, None)))
+    rec.keep.extend([x, w, ws, gamma, out, ws])
+    m = pm.Encoder(1, 64).eval()
+    plan = plans.LaunchPlan(rec, (x,), out, plans._Signature(m))
+    assert plan.n == 2 and [o.kind for o in plan.ops] == [1, 5]
+    assert plan.ops[0].linear.N == 192 and plan.ops[0].linear.out == ws.data_ptr()
+    ln = plan.ops[1]
+    assert ln.p[0] == ws.data_ptr() and ln.p[3] == out.data_ptr() + 64 and ln.p[4] is None
+    assert list(ln.i[:4]) == [192, 32, 64, 64] and abs(ln.f[0] - 1e-6) < 1e-12
+    in_slots, out_slots = plan.patches
+    assert sorted((f, off) for _, f, off in in_slots) == [("residual", 128), ("x", 0)]
+    assert [(f, off) for _, f, off in out_slots] == [(3, 64)]
+    kept = {t.data_ptr() for t in plan.keep}
+    assert kept == {w.data_ptr(), ws.data_ptr(), gamma.data_ptr()}            # not the caller's input / output
+    # patching writes through to the op array
+    for view, field, off in in_slots:
+        setattr(view, field, 0x5000 + off)
+    assert plan.ops[0].linear.x == 0x5000 and plan.ops[0].linear.residual == 0x5000 + 128
+    with pytest.raises(RuntimeError, match="no recorded launch writes the output"):
+        plans.LaunchPlan(rec, (x,), torch.zeros(3), plans._Signature(m))
