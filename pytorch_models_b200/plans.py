@@ -30,7 +30,7 @@ from . import _lib, ops
 
 ENABLED = os.environ.get("B200ENC_PLANS", "1") != "0"
 MAX_PLANS_PER_MODULE = 4
-STATS = {"recorded": 0, "replayed": 0, "unplannable": 0}
+STATS = {"recorded": 0, "replayed": 0, "unplannable": 0, "last_unplannable": None}
 _EPOCH = 0
 # module -> OrderedDict[key, LaunchPlan | None]. Kept OUTSIDE the module's __dict__: plans hold ctypes arrays and a lock,
 # which copy.deepcopy / pickle (EMA copies, torch.save(model)) must never meet; a copied module simply records its own.
@@ -260,7 +260,8 @@ def run(module: nn.Module, inputs: tuple[Tensor, ...], fn, extra_key: tuple = ()
             and sig.valid()):
         try:
             plan = LaunchPlan(rec, inputs, out, sig)
-        except RuntimeError:
+        except RuntimeError as e:  # e.g. the output is not written by any launch: stay on the per-call path
+            STATS["last_unplannable"] = f"{type(module).__name__}: {e}"
             plan = None
     STATS["recorded" if plan is not None else "unplannable"] += 1
     cache[key] = plan
