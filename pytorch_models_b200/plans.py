@@ -125,6 +125,12 @@ class LaunchPlan:
         self.lock = threading.Lock()
         self.out_shape, self.out_dtype, self.device = tuple(out.shape), out.dtype, out.device
         spans = [_span(t) for t in inputs] + [_span(out)]
+        for a in range(len(spans)):
+            for b in range(a + 1, len(spans)):
+                if spans[a][0] < spans[b][1] and spans[b][0] < spans[a][1]:
+                    # e.g. decoder(x, memory=x): a pointer inside both could not be attributed to one of them, and a later
+                    # call with two distinct tensors would be patched wrongly
+                    raise RuntimeError("the caller's tensors overlap in memory")
         # patch slots per input (and, last, for the output): (ctypes view, field name or index, byte offset)
         self.patches: list[list[tuple[object, object, int]]] = [[] for _ in spans]
         self._views: list[object] = []  # keeps the ctypes sub-objects the patch slots write through

@@ -190,3 +190,5 @@ def test_launch_plan_packs_a_recording_and_finds_the_patch_slots():
     assert plan.ops[0].linear.x == 0x5000 and plan.ops[0].linear.residual == 0x5000 + 128
     with pytest.raises(RuntimeError, match="no recorded launch writes the output"):
         plans.LaunchPlan(rec, (x,), torch.zeros(3), plans._Signature(m))
+    with pytest.raises(RuntimeError, match="overlap"):     # decoder(x, memory=x): pointers could not be attributed
+        plans.LaunchPlan(rec, (x, x[1:]), out, plans._Signature(m))
